@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the WESUP training step (BASELINE.json metric: train img/s at 464^2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Own arm: one "step" = `--images-per-step` full training iterations (GPU SLIC ->
+superpixel stats -> VGG16 -> hypercolumn -> pooling -> MLP -> label propagation
+-> loss -> backward -> [gradient all-reduce] -> SGD step) on 464x464 synthetic
+H&E-like images with 1e-4 point labels and random-init weights, batch-1 SGD as in
+the reference.  `value` is device-resident throughput; `e2e` goes through the
+public trainer API with pinned HOST inputs (H2D + loss D2H inside the timed
+region).  Prints ONE JSON line (rank 0).  The reference arm times the CPU oracle
+port (oracle/) of the same step on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+H = W = 464
+C_HYPER = 2112
+VGG_C = [32, 32, 64, 64, 128, 128, 128, 256, 256, 256, 256, 256, 256]
+VGG_SHIFT = [0, 0, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4]
+METRIC = "train img/s at 464x464 (WESUP weakly-supervised step: GPU SLIC + VGG16 + superpixel stage + loss + backward + SGD)"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------
+# clocks sampling
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores
+# ---------------------------------------------------------------------------
+def cpu_reference_step(model, img, point_mask, sgd):
+    """One reference training iteration on the CPU: SLIC (C restatement of
+    skimage) + _preprocess_superpixels + forward + loss + backward + SGD step,
+    all through the oracle's dense formulation (= the reference's algorithm)."""
+    import torch
+    from oracle import slic as oslic
+    from oracle import wesup_ref as O
+    seg = oslic.slic(img[0].permute(1, 2, 0).numpy(), int(H * W / 200), 40)
+    maps, labels, _ = O.preprocess_superpixels(torch.from_numpy(seg), point_mask[0])
+    sgd.zero_grad()
+    model((img, maps))
+    loss = O.compute_loss(model.sp_pred, model.sp_features, labels, propagate_threshold=0.8)
+    loss.backward()
+    sgd.step()
+    return float(loss.detach())
+
+
+def make_cpu_model():
+    import torch
+    from oracle import wesup_ref as O
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = O.seeded_init_(O.RefWESUP(), seed=0)
+    sgd = torch.optim.SGD(model.parameters(), lr=5e-5, momentum=0.9, weight_decay=1e-3)
+    return model, sgd
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                                   # CPU arm: rank 0 alone does the work
+    import torch
+    from wesup_b200 import synth
+    model, sgd = make_cpu_model()
+    data = [synth.sample(H, W, index=i) for i in range(2)]
+    for i in range(args.warmup):
+        cpu_reference_step(model, data[i % 2][0], data[i % 2][2], sgd)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        cpu_reference_step(model, data[i % 2][0], data[i % 2][2], sgd)
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    cores = torch.get_num_threads()
+    sample = "1 image (464x464) per step: C-SLIC + dense sp_maps + VGG16 fwd/bwd + dense mm pooling + loss + SGD, fp32"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "WESUP train step 464x464, batch-1 SGD, 1e-4 point labels, random-init VGG16",
+                       "images_per_step": 1, "device": "cpu"},
+            "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# own arm
+# ---------------------------------------------------------------------------
+def time_kernel(fn, iters, flush):
+    """Average device time of `fn` in ms over `iters` launches, CUDA events on the
+    current stream, an L2 flush (write of a > L2 buffer) before every launch."""
+    import torch
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    total = 0.0
+    for _ in range(iters):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        e.synchronize()
+        total += s.elapsed_time(e)
+    return total / iters
+
+
+def kernel_rooflines(dev, peak_gbs):
+    """Microbench of every superpixel-stage kernel at the workload's shape, timed
+    alone with CUDA events; algorithmic bytes per SURVEY.md section 8d / DESIGN.md."""
+    import torch
+    from wesup_b200 import ops, synth
+    from wesup_b200.ops import SuperpixelMaps
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    sides = [torch.randn(1, c, H >> s, W >> s, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+             for c, s in zip(VGG_C, VGG_SHIFT)]
+    side_bytes = sum(s.numel() * 4 for s in sides)
+    hw = H * W
+    out = {}
+    img, _, point_mask = synth.sample(H, W, index=0)
+    x = img.to(dev)
+    labels, n = ops.slic(x, int(hw / 200), 40)
+    n_sp = int(n.item())
+    sp = SuperpixelMaps.from_labels(labels, point_mask[0].to(dev), n_sp=n_sp)
+    for dtype, es, tag in ((torch.float32, 4, "f32"), (torch.bfloat16, 2, "bf16")):
+        feats = ops.hypercolumn(sides, (H, W), dtype=dtype)
+        ms = time_kernel(lambda: ops.hypercolumn(sides, (H, W), dtype=dtype), 10, flush)
+        b = side_bytes + C_HYPER * hw * es
+        out[f"hypercolumn_fwd_{tag}"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
+        ms = time_kernel(lambda: ops.sp_pool(feats, sp), 10, flush)
+        b = C_HYPER * hw * es + hw * 4 + n_sp * C_HYPER * 4 + n_sp * 4
+        out[f"sp_pool_fwd_{tag}"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
+        gp = torch.randn(n_sp, C_HYPER, device=dev)
+        gf = torch.empty_like(feats)
+        lib = ops._lib.load()
+        st = torch.cuda.current_stream().cuda_stream
+        code = ops._DTYPES[dtype]
+        ms = time_kernel(lambda: lib.wesup_sp_pool_bwd(gp.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(), hw,
+                                                       C_HYPER, n_sp, gf.data_ptr(), code, 1, st), 10, flush)
+        b = n_sp * C_HYPER * 4 + hw * 4 + C_HYPER * hw * es
+        out[f"sp_pool_bwd_{tag}"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
+        gsides = [torch.empty((1, s.size(2), s.size(3), s.size(1)), device=dev) for s in sides]
+        Cs, hs, ws_ = [s.size(1) for s in sides], [s.size(2) for s in sides], [s.size(3) for s in sides]
+        ptrs = ops._lib.ptr_array([t.data_ptr() for t in gsides])
+        ia = ops._lib.int_array
+        ms = time_kernel(lambda: lib.wesup_hypercolumn_bwd(gf.data_ptr(), code, 1, ia(Cs), ia(hs), ia(ws_), 13, H, W, ptrs, st),
+                         5, flush)
+        b = side_bytes + C_HYPER * hw * es
+        out[f"hypercolumn_bwd_{tag}"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
+        del feats, gf
+    ms = time_kernel(lambda: ops.slic(x, int(hw / 200), 40), 10, flush)
+    b = hw * 360
+    out["slic"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
+    ms = time_kernel(lambda: SuperpixelMaps.from_labels(labels, point_mask[0].to(dev), n_sp=n_sp), 10, flush)
+    out["sp_stats"] = {"ms": ms, "bytes": hw * 5 + n_sp * 12, "gbs": (hw * 5 + n_sp * 12) / ms / 1e6}
+    f = (torch.randn(n_sp, 32, device=dev) * 0.06).abs()
+    y_l = torch.zeros(sp.n_labeled, 2, device=dev); y_l[:, 0] = 1
+    ms = time_kernel(lambda: ops.label_propagate(f, y_l, 0.8), 10, flush)
+    out["label_propagate"] = {"ms": ms, "flops": 3.0 * (n_sp - sp.n_labeled) * sp.n_labeled * 32,
+                              "n": n_sp, "n_l": sp.n_labeled}
+    for v in out.values():
+        if "gbs" in v:
+            v["frac_of_hbm_peak"] = v["gbs"] / peak_gbs
+    return out
+
+
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    from wesup_b200 import _lib, parallel, synth
+    from wesup_b200.models import initialize_trainer
+    from wesup_b200.utils.metrics import accuracy, dice
+
+    rank, world, local = parallel.init_from_env("nccl")
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path for the own arm)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.manual_seed(0)
+    lib = _lib.load()
+    trainer = initialize_trainer("wesup", device=dev, pretrained=False)
+    trainer.optimizer, _ = trainer.get_default_optimizer()
+    trainer.metric_funcs = [accuracy, dice]
+    if world > 1:
+        trainer.enable_data_parallel()
+    ips = args.images_per_step
+    pool = max(ips, 4)
+    host = [synth.sample(H, W, index=rank * pool + i) for i in range(pool)]
+    host = [tuple(t.pin_memory() for t in s) for s in host]
+    resident = [tuple(t.to(dev) for t in s) for s in host]
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    def step_resident(i):
+        for j in range(ips):
+            trainer.train_one_iteration("train", *resident[(i * ips + j) % pool])
+
+    def step_host(i):
+        for j in range(ips):
+            trainer.train_one_iteration("train", *host[(i * ips + j) % pool])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.wesup_kernel_launches()
+        s.record()
+        for i in range(steps):
+            step_fn(i)
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), lib.wesup_kernel_launches() - l0
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches = timed(step_resident, args.steps)
+    for i in range(max(1, args.warmup // 2)):
+        step_host(i)
+    ms_e2e, _ = timed(step_host, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * ips * args.steps / (ms_total / 1e3)
+    e2e_value = world * ips * args.steps / (ms_e2e / 1e3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    kernels = kernel_rooflines(dev, peak) if not args.skip_kernels else {}
+    roofline = None
+    if kernels:
+        k = kernels["sp_pool_fwd_f32"]
+        traffic = None
+        tfile = ROOT / "profiles" / "roofline_traffic.json"
+        if tfile.exists():
+            traffic = json.loads(tfile.read_text()).get("sp_pool_fwd_f32")
+        roofline = {"kernel": "pool_fwd_hwc_kernel<float> (wesup_sp_pool_fwd)", "bound": "hbm", "achieved": k["gbs"],
+                    "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": k["gbs"] / peak, "traffic": traffic,
+                    "algorithmic_bytes_per_launch": k["bytes"], "ms_per_launch": k["ms"]}
+    cpu = None
+    if not args.skip_cpu:
+        model, sgd = make_cpu_model()
+        cpu_reference_step(model, *[synth.sample(H, W, index=1)[i] for i in (0, 2)], sgd)      # warm-up
+        t0 = time.perf_counter()
+        cpu_reference_step(model, *[synth.sample(H, W, index=0)[i] for i in (0, 2)], sgd)
+        dt = time.perf_counter() - t0
+        cpu = {"value": 1.0 / dt, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "1 training iteration on one 464x464 image after 1 warm-up iteration "
+                         "(C-SLIC + dense sp_maps + VGG16 + dense mm pooling + loss + backward + SGD, fp32)",
+               "host_cpus": os.cpu_count(), "seconds": dt}
+    line = {"metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "WESUP train step 464x464, batch-1 SGD, 1e-4 point labels, random-init VGG16",
+                       "images_per_step": ips, "images_per_step_all_ranks": ips * world, "hypercolumn": "f32 pixel-major (H*W,2112)",
+                       "parallelism": f"dp{world}", "l2": "working set 1.8 GB/image (hypercolumn) >> 126 MB L2; "
+                       "kernel microbenches flush L2 with a 256 MB write before every launch",
+                       "cudnn_tf32": bool(torch.backends.cudnn.allow_tf32)},
+            "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d * ips, "d2h_bytes_per_step": 4 * ips,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "kernels": kernels}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--images-per-step", type=int, default=4)
+    ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--skip-kernels", action="store_true", help="omit the per-kernel roofline microbench")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29517", __file__] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

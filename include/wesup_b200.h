@@ -1,0 +1,127 @@
+/* wesup_b200 -- C ABI of the B200-native WESUP superpixel stage.
+ *
+ * The reference (mrcfps/WESUP) is pure Python and has no FFI of its own; its
+ * boundary for this path is the Python surface of models/wesup.py.  This header
+ * is the native boundary *underneath* that surface: every entry point replaces
+ * the torch op sequence of one reference call site (cited per function).  The
+ * Python mirror in wesup_b200/models/wesup.py binds these with ctypes
+ * (wesup_b200/_lib.py); INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer on the current CUDA device unless the
+ *    comment says "host"; the caller owns all buffers including workspaces
+ *    (sizes from the *_workspace_bytes functions); nothing is allocated here;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *    never synchronises and is safe to capture in a CUDA graph;
+ *  - return value: 0 = OK, negative = bad argument (WESUP_E_*), positive = the
+ *    cudaError_t of a failed launch.  wesup_last_error() returns a thread-local
+ *    message for the most recent non-zero return on the calling thread;
+ *  - there is no CPU fallback: without a CUDA device every compute entry point
+ *    returns a cudaError_t.
+ */
+#ifndef WESUP_B200_H
+#define WESUP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WESUP_ABI_VERSION 1
+#define WESUP_MAX_LEVELS 16
+
+/* element type of the hypercolumn tensor */
+#define WESUP_F32 0
+#define WESUP_BF16 1
+/* layout of the hypercolumn / side tensors: channel-major (C,H,W) as in the
+ * reference (models/wesup.py:281) or pixel-major (H*W,C) (what the pooling
+ * gather and the pixel-inference GEMM, models/wesup.py:398, consume). */
+#define WESUP_CHW 0
+#define WESUP_HWC 1
+
+#define WESUP_E_ARG (-1)      /* null pointer / non-positive size */
+#define WESUP_E_UNSUPPORTED (-2) /* valid request outside what the kernels cover */
+#define WESUP_E_ALIGN (-3)    /* pointer or channel count breaks the 16-byte vector contract */
+
+int wesup_abi_version(void);
+const char *wesup_last_error(void);
+/* diagnostic: number of CUDA kernels this library has launched in this process
+ * (all threads); bench.py reports the delta over its timed region. */
+unsigned long long wesup_kernel_launches(void);
+
+/* ---- (a) hypercolumn: bilinear(align_corners=True) upsample + concat --------
+ * Replaces WESUP._hook_fn's F.interpolate + torch.cat chain
+ * (models/wesup.py:254-261) for all 13 side outputs in ONE launch.
+ * side[l]: fp32, (C[l],h[l],w[l]) for WESUP_CHW or (h[l],w[l],C[l]) for
+ * WESUP_HWC.  out: (sum C, H, W) or (H*W, sum C) in out_dtype.  `side`, `C`,
+ * `h`, `w` are HOST arrays of n_levels entries.  HWC needs C[l] % 4 == 0. */
+int wesup_hypercolumn_fwd(const void *const *side, const int *C, const int *h, const int *w,
+                          int n_levels, int H, int W, void *out, int out_dtype, int layout,
+                          void *stream);
+/* adjoint of the above (what autograd derives for models/wesup.py:254-261):
+ * grad_side[l] (fp32, same layout as side[l]) = bilinear^T of the level's
+ * channel slice of grad_out.  Deterministic (gather form, no atomics). */
+int wesup_hypercolumn_bwd(const void *grad_out, int grad_dtype, int layout, const int *C,
+                          const int *h, const int *w, int n_levels, int H, int W,
+                          void *const *grad_side, void *stream);
+
+/* ---- superpixel statistics: replaces _preprocess_superpixels ---------------
+ * (models/wesup.py:18-63) without the dense (N,H,W) maps.
+ * labels: (H*W) int32 ids in [0,n_sp).  mask: (n_cls,H,W) int64 one-hot-or-zero
+ * planes (utils/data.py:140-142,501-508) or NULL (= no supervision, :53-54).
+ * Outputs, all in the reference's row order "labeled ids ascending, then
+ * unlabeled ids ascending" (:45-47):
+ *   order[k]      original id of row k                           (n_sp)
+ *   row_labels[p] row index of pixel p (the relabelled map)      (H*W)
+ *   counts[k]     |S_k|                                          (n_sp)
+ *   seg_offsets   CSR offsets into seg_pixels                    (n_sp+1)
+ *   seg_pixels    pixel ids grouped by row, ascending inside     (H*W)
+ *   sp_labels     quantised multi-hot labels (:50-52), rows >= n_labeled zero (n_sp*n_cls)
+ *   n_labeled     device scalar */
+size_t wesup_sp_stats_workspace_bytes(int H, int W, int n_sp, int n_cls);
+int wesup_sp_stats(const int32_t *labels, const int64_t *mask, int H, int W, int n_cls, int n_sp,
+                   int32_t *order, int32_t *row_labels, int32_t *counts, int32_t *seg_offsets,
+                   int32_t *seg_pixels, float *sp_labels, int32_t *n_labeled, void *ws,
+                   void *stream);
+
+/* ---- (b) superpixel mean pooling -------------------------------------------
+ * fwd replaces torch.mm(sp_maps, x.t()) (models/wesup.py:284-285):
+ *   pooled[k,c] = mean_{p in S_k} feat[p,c]             pooled: (N,C) fp32
+ * bwd is the adjoint autograd derives for that mm:
+ *   grad_feat[p,c] = grad_pooled[row_labels[p],c] / counts[row_labels[p]] */
+int wesup_sp_pool_fwd(const void *feat, int dtype, int layout, const int32_t *seg_offsets,
+                      const int32_t *seg_pixels, int HW, int C, int N, float *pooled,
+                      void *stream);
+int wesup_sp_pool_bwd(const float *grad_pooled, const int32_t *row_labels, const int32_t *counts,
+                      int HW, int C, int N, void *grad_feat, int dtype, int layout, void *stream);
+
+/* ---- paint: replaces argmax + per-superpixel index_put loop -----------------
+ * (models/wesup.py:295-304): out[p] = sp_pred[row_labels[p], cls]. */
+int wesup_sp_paint(const int32_t *row_labels, const float *sp_pred, int HW, int n_cls, int cls,
+                   float *out, void *stream);
+
+/* ---- (c) label propagation: replaces _label_propagate ----------------------
+ * (models/wesup.py:99-139).  feats (N,D) fp32, rows [0,n_l) labeled;
+ * y_l (n_l,n_cls).  For every unlabeled row u: sim = exp(-min_j ||f_u-f_j||^2),
+ * src = first arg-max, y_u[u] = y_l[src] iff sim > thr (strict) else 0.
+ * y_u (N-n_l,n_cls); src_idx, max_sim (N-n_l) may be NULL. */
+size_t wesup_label_propagate_workspace_bytes(int N, int D, int n_l);
+int wesup_label_propagate(const float *feats, int N, int D, int n_l, const float *y_l, int n_cls,
+                          float thr, float *y_u, int32_t *src_idx, float *max_sim, void *ws,
+                          void *stream);
+
+/* ---- (d) SLIC: replaces skimage.segmentation.slic at models/wesup.py:471-476
+ * rgb: fp32 in [0,1], (3,H,W) for WESUP_CHW (what the trainer holds) or (H,W,3).
+ * labels: (H*W) int32, 0-based, contiguous, numbered in raster order of first
+ * pixel; n_labels: device scalar. */
+size_t wesup_slic_workspace_bytes(int H, int W, int n_segments);
+int wesup_slic(const float *rgb, int rgb_layout, int H, int W, int n_segments, double compactness,
+               int max_iter, int enforce_connectivity, int32_t *labels, int32_t *n_labels,
+               void *ws, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WESUP_B200_H */

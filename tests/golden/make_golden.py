@@ -43,6 +43,7 @@ def import_reference():
     sys.modules["skimage.transform"].resize = _absent
     sys.modules["skimage.measure"].label = _absent
     sys.modules["matplotlib"].use = lambda *a, **k: None
+    sys.modules["fire"].Fire = _absent
     import torchvision
     orig = torchvision.models.vgg16
     torchvision.models.vgg16 = lambda pretrained=False, **k: orig(weights=None)
@@ -161,6 +162,18 @@ def main():
     with torch.no_grad():
         pp = pix(x[:, :, :32, :32])
     np.savez(OUT / "pixel_inference_32x32.npz", img_u8=img_u8[:32, :32], pred=pp.numpy())
+    # ---- tile split / merge (infer_tile.py:23-91) -----------------------------
+    import infer_tile as ref_tile       # the real reference (fire / skimage.io are stubbed)
+    rng = np.random.default_rng(5)
+    tl = {}
+    for i, (h, w, p) in enumerate([(50, 37, 16), (40, 40, 20), (33, 70, 24)]):
+        img = rng.integers(0, 255, (h, w, 3), dtype=np.uint8)
+        patches = ref_tile.divide_image_to_patches(img, p)
+        preds = rng.random((len(patches), p, p))
+        tl[f"img{i}"], tl[f"patch{i}"], tl[f"patches{i}"], tl[f"preds{i}"] = img, np.int64(p), patches, preds
+        tl[f"combined{i}"] = ref_tile.combine_patches_to_image(preds, h, w)
+        tl[f"coords{i}"] = np.array(list(ref_tile._get_top_left_coordinates(h, w, p)))
+    np.savez_compressed(OUT / "tiles_cases.npz", **tl)
     print("golden vectors written to", OUT)
 
 

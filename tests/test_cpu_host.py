@@ -1,0 +1,172 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol the header
+declares, argument validation returns error codes without touching a GPU, the
+product path refuses to run without CUDA, and the host logic (sharding,
+gradient averaging over gloo, tile split/merge, synthetic data) works."""
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    from wesup_b200 import _lib
+    header = (ROOT / "include" / "wesup_b200.h").read_text()
+    declared = set(re.findall(r"\b(wesup_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.wesup_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(rf"\bT {name}\b", out), name
+
+
+def test_argument_validation_needs_no_gpu():
+    from wesup_b200 import _lib
+    lib = _lib.load()
+    assert lib.wesup_sp_paint(None, None, 10, 2, 1, None, None) == -1
+    assert b"null pointer" in lib.wesup_last_error()
+    assert lib.wesup_sp_pool_fwd(None, 0, 1, None, None, 10, 8, 2, None, None) == -1
+    assert lib.wesup_slic_workspace_bytes(464, 464, 1076) > 464 * 464 * 24
+    assert lib.wesup_slic_workspace_bytes(4, 4000, 10) == 0            # degenerate grid
+    assert lib.wesup_sp_stats_workspace_bytes(464, 464, 1076, 2) >= 1076 * 4 * 8
+    with pytest.raises(_lib.WesupNativeError):
+        _lib.check(-1, "demo")
+
+
+def test_product_path_has_no_cpu_fallback():
+    from wesup_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.SuperpixelMaps.from_labels(torch.zeros(4, 4, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.label_propagate(torch.zeros(4, 32), torch.zeros(2, 2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.slic(torch.zeros(3, 32, 32), 5)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.hypercolumn([torch.zeros(1, 4, 8, 8)], (8, 8))
+    src = "\n".join(p.read_text() for p in (ROOT / "wesup_b200").rglob("*.py"))
+    assert "import oracle" not in src and "from oracle" not in src    # the oracle is never on the product path
+
+
+def test_surface_and_state_dict_keys():
+    from wesup_b200.models import WESUP, WESUPConfig, WESUPPixelInference, initialize_trainer
+    from oracle.wesup_ref import RefWESUP
+    m = WESUP(pretrained=False)
+    assert list(m.state_dict()) == list(RefWESUP().state_dict())
+    assert list(WESUPPixelInference(pretrained=False).state_dict()) == list(m.state_dict())
+    cfg = WESUPConfig().to_dict()
+    assert cfg["sp_area"] == 200 and cfg["sp_compactness"] == 40 and cfg["propagate_threshold"] == 0.8
+    assert cfg["propagate_weight"] == 0.5 and cfg["epsilon"] == 1e-7 and cfg["batch_size"] == 1
+    trainer = initialize_trainer("wesup", device="cpu", pretrained=False)
+    opt, sched = trainer.get_default_optimizer()
+    assert sched is None and opt.defaults["lr"] == 5e-5 and opt.defaults["momentum"] == 0.9
+    with pytest.raises(ValueError):
+        initialize_trainer("mild")
+
+
+def test_cross_entropy_host_semantics(golden):
+    from wesup_b200.models.wesup import _cross_entropy
+    g = golden("cross_entropy_cases.npz")
+    yh, yt = torch.from_numpy(g["y_hat"]), torch.from_numpy(g["y_true"])
+    np.testing.assert_allclose(float(_cross_entropy(yh, yt)), float(g["loss"]), rtol=1e-6)
+    assert float(_cross_entropy(yh, torch.zeros_like(yt))) == 0.0
+
+
+def test_shard_range_partitions():
+    from wesup_b200.parallel import shard_range
+    for n in (0, 1, 7, 2500):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_tiles_split_and_merge_roundtrip():
+    from wesup_b200 import tiles
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 255, (130, 95, 3), dtype=np.uint8)
+    coords = tiles.top_left_coordinates(130, 95, 40)
+    assert len(coords) == 4 * 3 and coords[0] == (0, 0) and coords[-1] == (90, 55)
+    patches = tiles.divide_image_to_patches(img, 40)
+    assert patches.shape == (12, 40, 40, 3) and patches.dtype == np.uint8
+    merged = tiles.combine_patches_to_image(patches.astype(np.float64), 130, 95)
+    np.testing.assert_allclose(merged, img)                              # overlaps average identical values
+    exact = tiles.top_left_coordinates(20000, 20000, 400)
+    assert len(exact) == 2500 and exact[1] == (0, 400)
+
+
+WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from wesup_b200.parallel import GradientAllReduce, init_from_env, shard_range, gather_tiles
+rank, world, _ = init_from_env("gloo")
+torch.manual_seed(0)
+model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+sync = GradientAllReduce(model)
+with torch.no_grad():
+    for p in model.parameters():
+        p.add_(rank)                      # de-synchronise, then broadcast must repair it
+sync.broadcast_parameters()
+x = torch.arange(12, dtype=torch.float32).view(2, 6) + rank
+model(x).sum().backward()
+local = [p.grad.clone() for p in model.parameters()]
+sync.average_gradients()
+gathered = [None] * world
+dist.all_gather_object(gathered, [g.tolist() for g in local])
+mean = [sum(torch.tensor(g[i]) for g in gathered) / world for i in range(len(local))]
+ok = all(torch.allclose(p.grad, m, atol=1e-6) for p, m in zip(model.parameters(), mean))
+ok = ok and all(p.grad.data_ptr() >= sync.flat.data_ptr() for p in model.parameters())
+lo, hi = shard_range(7, rank, world)
+tiles = torch.arange(lo, hi, dtype=torch.float32).view(-1, 1, 1).expand(-1, 2, 2).contiguous()
+full = gather_tiles(tiles, 7, rank, world)
+if rank == 0:
+    ok = ok and full.shape == (7, 2, 2) and full[:, 0, 0].tolist() == list(range(7))
+print("RANK", rank, "OK" if ok else "FAIL")
+dist.destroy_process_group()
+"""
+
+
+def test_gradient_allreduce_and_tile_gather_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=str(ROOT)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "RANK 0 OK" in r.stdout and "RANK 1 OK" in r.stdout, r.stdout + r.stderr[-2000:]
+
+
+def test_synthetic_data_contract():
+    from wesup_b200 import synth
+    img, pixel_mask, point_mask = synth.sample(64, 80, index=0, ratio=1e-3)
+    assert img.shape == (1, 3, 64, 80) and img.dtype == torch.float32 and 0 <= float(img.min()) and float(img.max()) <= 1
+    assert pixel_mask.shape == (1, 2, 64, 80) and pixel_mask.dtype == torch.int64
+    assert torch.all(pixel_mask.sum(1) == 1)
+    assert int(point_mask.sum()) == max(2, int(64 * 80 * 1e-3)) and int(point_mask.sum(1).max()) == 1
+    again = synth.sample(64, 80, index=0, ratio=1e-3)
+    assert all(torch.equal(a, b) for a, b in zip((img, pixel_mask, point_mask), again))
+    seg = synth.perturbed_grid_segments(40, 40, 8, seed=0)
+    assert seg.min() == 0 and len(np.unique(seg)) == seg.max() + 1
+
+
+def test_tiles_match_reference_golden(golden):
+    from wesup_b200 import tiles
+    g = golden("tiles_cases.npz")
+    for i in range(3):
+        img, p = g[f"img{i}"], int(g[f"patch{i}"])
+        h, w, _ = img.shape
+        assert np.array_equal(np.array(tiles.top_left_coordinates(h, w, p)), g[f"coords{i}"])
+        assert np.array_equal(tiles.divide_image_to_patches(img, p), g[f"patches{i}"])
+        merged = tiles.combine_patches_to_image(g[f"preds{i}"], h, w)
+        assert np.array_equal(merged, g[f"combined{i}"])          # same arithmetic order => bit-exact

@@ -1,0 +1,351 @@
+"""GPU parity tests: every kernel behind the C ABI against the CPU oracle
+(oracle/wesup_ref.py, oracle/slic_ref.c) and the golden vectors minted from the
+real reference.  Tolerances follow BASELINE.json's north star: index/assignment
+results bit-exact, pooled features and loss 1e-4 relative in fp32 (1e-2 bf16),
+SLIC >= 99 % pixel agreement."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import wesup_ref as O                      # noqa: E402
+from oracle import slic as oslic                       # noqa: E402
+from wesup_b200 import ops, synth                      # noqa: E402
+from wesup_b200.ops import SuperpixelMaps              # noqa: E402
+
+DEV = "cuda"
+VGG_C = [32, 32, 64, 64, 128, 128, 128, 256, 256, 256, 256, 256, 256]
+VGG_SHIFT = [0, 0, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4]
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def make_sides(h, w, seed=0, channels=VGG_C, shifts=VGG_SHIFT):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(1, c, h >> s, w >> s, generator=g) for c, s in zip(channels, shifts)]
+
+
+# ---------------------------------------------------------------------------
+# sp_stats (a2)
+# ---------------------------------------------------------------------------
+def check_stats(seg_np, mask_t):
+    seg = torch.from_numpy(seg_np)
+    maps, labels, order = O.preprocess_superpixels(seg, mask_t)
+    sp = SuperpixelMaps.from_labels(seg.to(DEV), None if mask_t is None else mask_t.to(DEV))
+    assert sp.order.cpu().tolist() == order.tolist()                      # bit-exact ordering
+    counts = (maps > 0).sum(dim=(1, 2))
+    assert sp.counts.cpu().tolist() == counts.tolist()
+    owner = maps.argmax(dim=0)
+    assert torch.equal(sp.label_map.cpu().long(), owner)
+    offs = sp.seg_offsets.cpu().long()
+    assert offs[0] == 0 and offs[-1] == seg.numel()
+    assert torch.equal(offs[1:] - offs[:-1], counts)
+    px = sp.seg_pixels.cpu().long()
+    flat_owner = owner.reshape(-1)
+    for k in range(sp.n):
+        mine = px[offs[k]:offs[k + 1]]
+        assert torch.all(flat_owner[mine] == k)
+        assert torch.all(mine[1:] > mine[:-1])                            # ascending => deterministic sums
+    if mask_t is None:
+        assert sp.sp_labels is None
+    else:
+        assert sp.n_labeled == labels.size(0)
+        assert torch.equal(sp.sp_labels.cpu(), labels)                     # bit-exact multi-hot labels
+    return sp
+
+
+def test_stats_kat_and_golden(golden):
+    g = golden("kat_preprocess_4x4.npz")
+    sp = check_stats(g["segments"], torch.from_numpy(g["mask"]))
+    assert sp.order.cpu().tolist() == [0, 2, 1, 3]
+    assert sp.sp_labels.cpu().tolist() == [[1.0, 1.0], [0.0, 1.0]]
+    np.testing.assert_allclose(sp.to_dense().cpu().numpy(), g["sp_maps"], rtol=0, atol=0)
+    c = golden("preprocess_cases.npz")
+    for i in range(3):
+        sp = check_stats(c[f"seg{i}"], torch.from_numpy(c[f"mask{i}"]))
+        assert sp.order.cpu().tolist() == c[f"order{i}"].tolist()
+        assert sp.counts.cpu().tolist() == c[f"counts{i}"].tolist()
+        np.testing.assert_array_equal(sp.sp_labels.cpu().numpy(), c[f"labels{i}"])
+        sp_n = check_stats(c[f"seg{i}"], None)
+        assert sp_n.order.cpu().tolist() == c[f"order_none{i}"].tolist()
+
+
+@pytest.mark.parametrize("h,w,n", [(1, 7, 3), (5, 1, 2), (37, 53, 40), (64, 64, 1000), (128, 96, 7)])
+def test_stats_random_label_maps(h, w, n):
+    rng = np.random.default_rng(h * 1000 + w)
+    seg = rng.integers(0, n, size=(h, w))
+    _, seg = np.unique(seg, return_inverse=True)        # contiguous ids, every id present
+    seg = seg.reshape(h, w)
+    k = int(seg.max()) + 1
+    if k < 2:
+        pytest.skip("reference needs N >= 2 (squeeze at models/wesup.py:58)")
+    mask = torch.zeros(3, h, w, dtype=torch.int64)
+    pick = rng.random((h, w)) < 0.2
+    cls = rng.integers(0, 3, size=(h, w))
+    for c in range(3):
+        mask[c][torch.from_numpy(pick & (cls == c))] = 1
+    check_stats(seg, mask)
+    check_stats(seg, None)
+
+
+def test_stats_full_mask_and_single_pixel_superpixels():
+    seg = np.arange(6 * 9).reshape(6, 9)                # every superpixel is one pixel
+    _, gland = synth.he_like_image(6, 9, seed=5)
+    check_stats(seg, synth.pixel_mask(gland))
+
+
+# ---------------------------------------------------------------------------
+# pooling (a4) + paint (a6)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("layout", ["hwc", "chw"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+def test_pool_fwd_bwd_vs_dense_mm(layout, dtype, tol):
+    h, w, c = 45, 61, 132
+    seg = synth.perturbed_grid_segments(h, w, 7, seed=3)
+    maps, _, _ = O.preprocess_superpixels(torch.from_numpy(seg), None)
+    g = torch.Generator().manual_seed(1)
+    feat_chw = torch.randn(c, h, w, generator=g)
+    ref_in = feat_chw.to(dtype).float().requires_grad_(True)       # oracle sees the same rounded inputs
+    ref = O.pool_dense(maps, ref_in)
+    grad = torch.randn(ref.shape, generator=g)
+    ref.backward(grad)
+    sp = SuperpixelMaps.from_labels(torch.from_numpy(seg).to(DEV))
+    if layout == "hwc":
+        x = feat_chw.permute(1, 2, 0).reshape(h * w, c).to(DEV, dtype).contiguous().requires_grad_(True)
+    else:
+        x = feat_chw.to(DEV, dtype).contiguous().requires_grad_(True)
+    out = ops.sp_pool(x, sp, layout=layout)
+    assert out.dtype == torch.float32 and out.shape == ref.shape
+    assert rel_err(out.cpu(), ref.detach()) < max(tol, 2e-6)
+    out.backward(grad.to(DEV))
+    gx = x.grad.float().cpu()
+    gx = gx.view(h, w, c).permute(2, 0, 1) if layout == "hwc" else gx
+    assert rel_err(gx, ref_in.grad) < tol
+    # run twice: the gather is deterministic, results must be bit-identical
+    out2 = ops.sp_pool(x.detach(), sp, layout=layout)
+    assert torch.equal(out2, out.detach())
+
+
+def test_pool_large_properties():
+    """Full 464x464 x 2112 shape: size-independent properties instead of the dense
+    oracle (the reference's one-hot mm would need 0.93 GB + 0.98 TFLOP on the CPU)."""
+    h = w = 464
+    c = 2112
+    seg = synth.perturbed_grid_segments(h, w, 14, seed=11)
+    sp = SuperpixelMaps.from_labels(torch.from_numpy(seg).to(DEV))
+    feat = torch.randn(h * w, c, device=DEV)
+    pooled = ops.sp_pool(feat, sp)
+    # (1) count-weighted sum of means == global sum (linearity / partition of unity)
+    total = (pooled.double() * sp.counts.double().unsqueeze(1)).sum(0)
+    assert rel_err(total, feat.double().sum(0)) < 1e-6
+    # (2) a feature that is constant inside every superpixel pools to itself, exactly
+    const = sp.row_labels.float().unsqueeze(1).expand(-1, 8).contiguous()
+    pc = ops.sp_pool(const, sp)
+    assert rel_err(pc, torch.arange(sp.n, device=DEV, dtype=torch.float32).unsqueeze(1).expand(-1, 8)) < 1e-6
+    # (3) spot-check 16 rows against a direct mean
+    lab = sp.row_labels.long()
+    for k in np.random.default_rng(0).integers(0, sp.n, 16):
+        ref = feat[lab == int(k)].double().mean(0)
+        assert rel_err(pooled[int(k)], ref) < 1e-6
+    # (4) adjoint identity <pool(x), g> == <x, pool^T(g)>
+    x = feat[:, :64].contiguous().requires_grad_(True)
+    gp = torch.randn(sp.n, 64, device=DEV)
+    y = ops.sp_pool(x, sp)
+    y.backward(gp)
+    lhs = (y.detach().double() * gp.double()).sum()
+    rhs = (x.detach().double() * x.grad.double()).sum()
+    assert abs(float(lhs - rhs)) < 1e-6 * abs(float(lhs)) + 1e-6
+
+
+def test_paint_matches_reference_loop():
+    h, w = 40, 56
+    seg = synth.perturbed_grid_segments(h, w, 8, seed=10)
+    maps, _, _ = O.preprocess_superpixels(torch.from_numpy(seg), None)
+    pred = torch.softmax(torch.randn(maps.size(0), 2, generator=torch.Generator().manual_seed(2)), dim=1)
+    ref = O.paint_dense(maps, pred)
+    sp = SuperpixelMaps.from_labels(torch.from_numpy(seg).to(DEV))
+    out = ops.paint(sp, pred.to(DEV), cls=1)
+    assert out.shape == ref.shape
+    assert torch.equal(out.cpu(), ref)                   # pure gather: bit-exact
+
+
+def test_dense_sp_maps_are_accepted():
+    seg = synth.perturbed_grid_segments(24, 30, 6, seed=4)
+    maps, _, _ = O.preprocess_superpixels(torch.from_numpy(seg), None)
+    sp = SuperpixelMaps.from_dense(maps.to(DEV))
+    assert sp.n == maps.size(0)
+    assert torch.equal(sp.label_map.cpu().long(), maps.argmax(0))
+
+
+# ---------------------------------------------------------------------------
+# hypercolumn (a3)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("layout", ["hwc", "chw"])
+@pytest.mark.parametrize("h,w", [(48, 40), (37, 51), (16, 16)])
+def test_hypercolumn_fwd_bwd_vs_interpolate(layout, h, w):
+    sides = make_sides(h, w, seed=h)
+    ref_in = [s.clone().requires_grad_(True) for s in sides]
+    ref = O.hypercolumn_from_sides(ref_in, (h, w))                       # (C,H,W)
+    grad = torch.randn(ref.shape, generator=torch.Generator().manual_seed(9))
+    ref.backward(grad)
+    xs = [s.to(DEV).requires_grad_(True) for s in sides]
+    out = ops.hypercolumn(xs, (h, w), layout=layout)
+    got = out.cpu().view(h, w, -1).permute(2, 0, 1) if layout == "hwc" else out.cpu()
+    assert rel_err(got, ref.detach()) < 1e-6
+    np.testing.assert_allclose(got.numpy(), ref.detach().numpy(), rtol=1e-4, atol=1e-5)
+    # identity levels are exact copies
+    assert torch.equal(got[:32], sides[0][0])
+    g_dev = grad.permute(1, 2, 0).reshape(h * w, -1).contiguous() if layout == "hwc" else grad
+    out.backward(g_dev.to(DEV))
+    for x, r in zip(xs, ref_in):
+        assert rel_err(x.grad.cpu(), r.grad) < 1e-5
+
+
+def test_hypercolumn_bf16_and_golden_probe(golden):
+    g = golden("forward_loss_backward_48x40.npz")
+    model = O.seeded_init_(O.RefWESUP(), seed=3)
+    x = synth.to_tensor(g["img_u8"]).unsqueeze(0)
+    with torch.no_grad():
+        sides = model.side_outputs(x)
+    out = ops.hypercolumn([s.to(DEV) for s in sides], (48, 40))
+    got = out.cpu().view(48, 40, -1).permute(2, 0, 1)
+    np.testing.assert_allclose(got[:, ::7, ::5].numpy(), g["feats_probe"], rtol=1e-4, atol=1e-5)
+    out16 = ops.hypercolumn([s.to(DEV) for s in sides], (48, 40), dtype=torch.bfloat16)
+    assert out16.dtype == torch.bfloat16
+    assert rel_err(out16.float().cpu(), out.cpu()) < 1e-2
+
+
+def test_hypercolumn_adjoint_identity_full_size():
+    h = w = 464
+    xs = [s.to(DEV).requires_grad_(True) for s in make_sides(h, w, seed=1)]
+    out = ops.hypercolumn(xs, (h, w))
+    assert out.shape == (h * w, 2112)
+    g = torch.randn_like(out)
+    out.backward(g)
+    lhs = (out.detach().double() * g.double()).sum()
+    rhs = sum((x.detach().double() * x.grad.double()).sum() for x in xs)
+    assert abs(float(lhs - rhs)) < 1e-6 * abs(float(lhs)) + 1e-3
+    # partition of unity: constant sides upsample to the same constant
+    ones = [torch.full_like(x, 2.5) for x in xs]
+    const = ops.hypercolumn(ones, (h, w))
+    assert float((const - 2.5).abs().max()) < 1e-5
+
+
+# ---------------------------------------------------------------------------
+# label propagation (a7)
+# ---------------------------------------------------------------------------
+def check_propagation(f, y_l, thr):
+    """Bit-exact in src index and propagated/not decision wherever the decision
+    is numerically unambiguous; rows whose top-2 similarities (or whose
+    similarity and the threshold) are closer than 4 fp32 ulp may legitimately
+    differ between two fp32 evaluation orders (the reference's own einsum order
+    is backend-dependent) and are only required to pick one of the tied answers."""
+    y_u_ref, src_ref, sim_ref = O.label_propagate(f, y_l, thr, return_aux=True)
+    y_u, src, sim = ops.label_propagate(f.to(DEV), y_l.to(DEV), thr, return_aux=True)
+    y_u, src, sim = y_u.cpu(), src.cpu().long(), sim.cpu()
+    n_l = y_l.size(0)
+    d2 = torch.cdist(f[n_l:].double(), f[:n_l].double()) ** 2
+    w_all = torch.exp(-d2)
+    top2 = w_all.topk(min(2, n_l), dim=1).values
+    eps = 4 * 1.2e-7
+    ambiguous_src = (top2[:, 0] - top2[:, -1] < eps * top2[:, 0]) if n_l > 1 else torch.zeros(len(src), dtype=torch.bool)
+    ambiguous_thr = (top2[:, 0] - thr).abs() < eps
+    clear = ~ambiguous_src
+    assert torch.equal(src[clear], src_ref[clear])
+    tied = torch.nonzero(ambiguous_src).flatten()
+    for u in tied.tolist():
+        assert w_all[u, src[u]] >= top2[u, 0] - eps
+    ok_rows = clear & ~ambiguous_thr
+    assert torch.equal(y_u[ok_rows], y_u_ref[ok_rows])
+    assert torch.allclose(sim, sim_ref, rtol=1e-5, atol=1e-7)
+    return int(clear.sum()), len(src)
+
+
+def test_label_propagate_golden(golden):
+    g = golden("label_propagate_cases.npz")
+    for i in range(4):
+        f, yl = torch.from_numpy(g[f"f{i}"]), torch.from_numpy(g[f"yl{i}"])
+        for thr in (0.8, 0.95):
+            y_u = ops.label_propagate(f.to(DEV), yl.to(DEV), thr).cpu()
+            np.testing.assert_array_equal(y_u.numpy(), g[f"yu{i}_{int(thr * 100)}"])
+            check_propagation(f, yl, thr)
+
+
+@pytest.mark.parametrize("n,n_l,scale", [(300, 1, 0.06), (1076, 21, 0.06), (2022, 40, 0.06), (1500, 750, 0.05), (4000, 2000, 0.06)])
+def test_label_propagate_vs_oracle(n, n_l, scale):
+    g = torch.Generator().manual_seed(n)
+    f = (torch.randn(n, 32, generator=g) * scale).abs()
+    y_l = torch.zeros(n_l, 2)
+    y_l[torch.arange(n_l), torch.randint(0, 2, (n_l,), generator=g)] = 1
+    clear, total = check_propagation(f, y_l, 0.8)
+    assert clear >= 0.99 * total
+
+
+def test_label_propagate_edge_cases():
+    f = torch.zeros(10, 32)
+    f[:, 0] = torch.arange(10).float() * 0.1
+    y_l = torch.tensor([[1.0, 0.0], [0.0, 1.0], [1.0, 1.0]])
+    # identical features: tie -> lowest labeled index
+    same = torch.ones(6, 32) * 0.3
+    y_u, src, sim = ops.label_propagate(same.to(DEV), y_l.to(DEV), 0.8, return_aux=True)
+    assert src.cpu().tolist() == [0, 0, 0] and torch.all(sim.cpu() == 1.0)
+    assert y_u.cpu().tolist() == [[1.0, 0.0]] * 3
+    # sim == fp32(thr) is NOT propagated (strict >)
+    thr = float(torch.tensor(1.0))
+    y_u = ops.label_propagate(same.to(DEV), y_l.to(DEV), thr)
+    assert float(y_u.sum()) == 0.0
+    # multi-hot labeled rows are copied as they are
+    f2 = torch.zeros(5, 32)
+    f2[3:, 1] = 0.01
+    f2[2, 1] = 0.01
+    y_u = ops.label_propagate(f2.to(DEV), y_l.to(DEV), 0.5)
+    assert y_u.cpu().tolist() == [[1.0, 1.0], [1.0, 1.0]]
+    # no unlabeled rows -> empty result
+    assert ops.label_propagate(f2[:3].to(DEV), y_l.to(DEV), 0.5).shape == (0, 2)
+
+
+# ---------------------------------------------------------------------------
+# SLIC (a1)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("h,w,seed", [(96, 128, 1), (131, 97, 2), (464, 464, 1000)])
+def test_slic_agreement_with_cpu_restatement(h, w, seed):
+    img_u8, _ = synth.he_like_image(h, w, seed=seed)
+    img = img_u8.astype(np.float32) / 255.0
+    n_segments = int(h * w / 200)
+    ref_labels, ref_raw, _, ref_n = oslic.slic(img, n_segments, 40, return_aux=True)
+    x = torch.from_numpy(img.transpose(2, 0, 1).copy()).to(DEV)
+    raw, k = ops.slic(x, n_segments, 40, enforce_connectivity=False)
+    raw_agree = float((raw.cpu().numpy() == ref_raw).mean())
+    assert raw_agree >= 0.99, f"k-means assignment agreement {raw_agree:.4f}"
+    labels, n = ops.slic(x, n_segments, 40)
+    labels = labels.cpu().numpy()
+    # both sides number labels 0..n-1 in raster order of first pixel, so ids are directly comparable
+    agree = float((labels == ref_labels).mean())
+    assert agree >= 0.99, f"label agreement {agree:.4f}"
+    n = int(n.item())
+    assert labels.min() == 0 and labels.max() == n - 1
+    assert len(np.unique(labels)) == n                     # contiguous ids, as the reference requires
+    assert abs(n - ref_n) <= max(2, 0.01 * ref_n)
+    first = [np.argmax(labels.reshape(-1) == i) for i in range(n)]
+    assert first == sorted(first)                          # raster-order numbering
+
+
+def test_slic_connectivity_matches_sequential_on_kmeans_output():
+    """Feed the CPU oracle's raw k-means assignment through both connectivity
+    implementations: isolates the CCL/merge kernels from fp differences."""
+    h, w = 200, 232
+    img_u8, _ = synth.he_like_image(h, w, seed=77)
+    img = img_u8.astype(np.float32) / 255.0
+    n_segments = int(h * w / 200)
+    x = torch.from_numpy(img.transpose(2, 0, 1).copy()).to(DEV)
+    raw, _ = ops.slic(x, n_segments, 40, enforce_connectivity=False)
+    seg_size = h * w / n_segments
+    ref, ref_n = oslic.connectivity(raw.cpu().numpy(), int(0.5 * seg_size), int(3 * seg_size))
+    labels, n = ops.slic(x, n_segments, 40)
+    assert float((labels.cpu().numpy() == ref).mean()) >= 0.999
+    assert int(n.item()) == ref_n

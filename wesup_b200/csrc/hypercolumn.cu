@@ -1,0 +1,265 @@
+// (a) Hypercolumn construction: bilinear (align_corners=True) upsampling of the
+// 13 VGG16 side outputs to the input size, concatenated along channels, written
+// ONCE.  Replaces WESUP._hook_fn's interpolate + 12 incremental torch.cat calls
+// (/root/reference/models/wesup.py:246-261), which re-copy the growing tensor
+// (5x the final bytes).
+//
+// Layouts: pixel-major (H*W, C) is the primary one -- a warp writes 512
+// contiguous bytes of one pixel (128-bit stores, full cache lines) and the
+// low-resolution taps are contiguous channel vectors served from L1/L2.
+// Channel-major (C,H,W) (the reference's layout) is also provided.
+//
+// Backward is the exact adjoint in gather form (each low-resolution element
+// sums its footprint in a fixed order): deterministic, no atomics.
+#include "common.cuh"
+
+namespace wesup {
+
+struct Levels {
+    const float *src[WESUP_MAX_LEVELS];   // fwd: side outputs; bwd: unused
+    float *dst[WESUP_MAX_LEVELS];         // bwd: side gradients
+    int C[WESUP_MAX_LEVELS], h[WESUP_MAX_LEVELS], w[WESUP_MAX_LEVELS], coff[WESUP_MAX_LEVELS];
+    float sy[WESUP_MAX_LEVELS], sx[WESUP_MAX_LEVELS];
+    int n, H, W, Ctot;
+};
+
+constexpr int TILE_W = 16, TILE_H = 4, TILE_PX = TILE_W * TILE_H;
+
+// ---------------------------------------------------------------------------
+// forward, pixel-major.  Block = one 4x16 pixel tile; for every level the
+// block's threads sweep (pixel, 4-channel group) items with the channel group
+// fastest, so each warp store covers whole 128-byte lines of the output.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) hyper_fwd_hwc_kernel(const Levels L, T *__restrict__ out) {
+    const int tx0 = blockIdx.x * TILE_W, ty0 = blockIdx.y * TILE_H;
+    const int tid = threadIdx.x;
+    for (int l = 0; l < L.n; ++l) {
+        const int Cl = L.C[l], c4n = Cl >> 2, hl = L.h[l], wl = L.w[l];
+        const float *__restrict__ src = L.src[l];
+        const float sy = L.sy[l], sx = L.sx[l];
+        const bool identity = (hl == L.H && wl == L.W);
+        const int items = TILE_PX * c4n;
+        for (int it = tid; it < items; it += 256) {
+            int px = it / c4n;
+            int c = (it - px * c4n) << 2;
+            int y = ty0 + px / TILE_W, x = tx0 + (px % TILE_W);
+            if (y >= L.H || x >= L.W) continue;
+            float4 v;
+            if (identity) {
+                v = ldg_stream(reinterpret_cast<const float4 *>(src + ((long)y * wl + x) * Cl + c));
+            } else {
+                Tap ty = bilinear_tap(y, sy, hl), tx = bilinear_tap(x, sx, wl);
+                const float *r0 = src + (long)ty.i0 * wl * Cl + c;
+                const float *r1 = src + (long)ty.i1 * wl * Cl + c;
+                float4 v00 = __ldg(reinterpret_cast<const float4 *>(r0 + (long)tx.i0 * Cl));
+                float4 v01 = __ldg(reinterpret_cast<const float4 *>(r0 + (long)tx.i1 * Cl));
+                float4 v10 = __ldg(reinterpret_cast<const float4 *>(r1 + (long)tx.i0 * Cl));
+                float4 v11 = __ldg(reinterpret_cast<const float4 *>(r1 + (long)tx.i1 * Cl));
+                float4 top = tx.w0 * v00; fma4(top, tx.w1, v01);
+                float4 bot = tx.w0 * v10; fma4(bot, tx.w1, v11);
+                v = ty.w0 * top; fma4(v, ty.w1, bot);
+            }
+            Vec4<T>::store(out + ((long)y * L.W + x) * L.Ctot + L.coff[l] + c, v);
+        }
+    }
+}
+
+// forward, channel-major: one thread per (channel, y, 4 consecutive x)
+template <typename T>
+__global__ void __launch_bounds__(256) hyper_fwd_chw_kernel(const Levels L, T *__restrict__ out) {
+    const int l = blockIdx.z;
+    const int Cl = L.C[l], hl = L.h[l], wl = L.w[l];
+    const int W4 = (L.W + 3) >> 2;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = (long)Cl * L.H * W4;
+    if (idx >= total) return;
+    int x4 = (int)(idx % W4);
+    long t = idx / W4;
+    int y = (int)(t % L.H), c = (int)(t / L.H);
+    const float *__restrict__ plane = L.src[l] + (long)c * hl * wl;
+    Tap ty = bilinear_tap(y, L.sy[l], hl);
+    T *o = out + ((long)(L.coff[l] + c) * L.H + y) * L.W;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int x = x4 * 4 + j;
+        if (x >= L.W) break;
+        Tap tx = bilinear_tap(x, L.sx[l], wl);
+        float top = tx.w0 * __ldg(plane + (long)ty.i0 * wl + tx.i0);
+        top = fmaf(tx.w1, __ldg(plane + (long)ty.i0 * wl + tx.i1), top);
+        float bot = tx.w0 * __ldg(plane + (long)ty.i1 * wl + tx.i0);
+        bot = fmaf(tx.w1, __ldg(plane + (long)ty.i1 * wl + tx.i1), bot);
+        o[x] = static_cast<T>(fmaf(ty.w1, bot, ty.w0 * top));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// backward (adjoint), gather form.  For low-res index i, the output indices d
+// whose taps touch i form a contiguous range; it is bracketed conservatively
+// and every candidate is tested with the *same* fp32 tap arithmetic as the
+// forward, so fwd and bwd are exact adjoints of each other.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void footprint(int i, float scale, int out_size, int &lo, int &hi) {
+    if (scale <= 0.f) { lo = 0; hi = out_size - 1; return; }
+    float inv = 1.0f / scale;
+    lo = (int)floorf((float)(i - 1) * inv) - 1;
+    hi = (int)ceilf((float)(i + 1) * inv) + 1;
+    lo = max(lo, 0);
+    hi = min(hi, out_size - 1);
+}
+__device__ __forceinline__ float tap_weight(int d, int i, float scale, int in_size) {
+    Tap t = bilinear_tap(d, scale, in_size);
+    float wgt = 0.f;
+    if (t.i0 == i) wgt += t.w0;
+    if (t.i1 == i) wgt += t.w1;
+    return wgt;
+}
+
+// pixel-major: one thread per (level, low-res pixel, 4-channel group)
+template <typename T>
+__global__ void __launch_bounds__(256) hyper_bwd_hwc_kernel(const Levels L, const T *__restrict__ grad_out) {
+    const int l = blockIdx.y;
+    const int Cl = L.C[l], c4n = Cl >> 2, hl = L.h[l], wl = L.w[l];
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = (long)hl * wl * c4n;
+    if (idx >= total) return;
+    int c = ((int)(idx % c4n)) << 2;
+    long q = idx / c4n;
+    int j = (int)(q % wl), i = (int)(q / wl);
+    const T *g = grad_out + L.coff[l] + c;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (hl == L.H && wl == L.W) {
+        acc = Vec4<T>::load(g + ((long)i * L.W + j) * L.Ctot);
+    } else {
+        int ylo, yhi, xlo, xhi;
+        footprint(i, L.sy[l], L.H, ylo, yhi);
+        footprint(j, L.sx[l], L.W, xlo, xhi);
+        for (int y = ylo; y <= yhi; ++y) {
+            float wy = tap_weight(y, i, L.sy[l], hl);
+            if (wy == 0.f) continue;
+            float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int x = xlo; x <= xhi; ++x) {
+                float wx = tap_weight(x, j, L.sx[l], wl);
+                if (wx == 0.f) continue;
+                fma4(row, wx, Vec4<T>::load_cached(g + ((long)y * L.W + x) * L.Ctot));
+            }
+            fma4(acc, wy, row);
+        }
+    }
+    *reinterpret_cast<float4 *>(L.dst[l] + ((long)i * wl + j) * Cl + c) = acc;
+}
+
+// channel-major: one thread per (level, channel, low-res pixel)
+template <typename T>
+__global__ void __launch_bounds__(256) hyper_bwd_chw_kernel(const Levels L, const T *__restrict__ grad_out) {
+    const int l = blockIdx.y;
+    const int Cl = L.C[l], hl = L.h[l], wl = L.w[l];
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long total = (long)Cl * hl * wl;
+    if (idx >= total) return;
+    int j = (int)(idx % wl);
+    long t = idx / wl;
+    int i = (int)(t % hl), c = (int)(t / hl);
+    const T *plane = grad_out + (long)(L.coff[l] + c) * L.H * L.W;
+    float acc = 0.f;
+    int ylo, yhi, xlo, xhi;
+    footprint(i, L.sy[l], L.H, ylo, yhi);
+    footprint(j, L.sx[l], L.W, xlo, xhi);
+    for (int y = ylo; y <= yhi; ++y) {
+        float wy = tap_weight(y, i, L.sy[l], hl);
+        if (wy == 0.f) continue;
+        float row = 0.f;
+        for (int x = xlo; x <= xhi; ++x) {
+            float wx = tap_weight(x, j, L.sx[l], wl);
+            if (wx == 0.f) continue;
+            row = fmaf(wx, (float)plane[(long)y * L.W + x], row);
+        }
+        acc = fmaf(wy, row, acc);
+    }
+    L.dst[l][idx] = acc;
+}
+
+static int fill_levels(Levels &L, const char *who, const int *C, const int *h, const int *w, int n_levels, int H, int W,
+                       int layout) {
+    WESUP_REQUIRE(C && h && w, WESUP_E_ARG, "%s: null geometry", who);
+    WESUP_REQUIRE(n_levels > 0 && n_levels <= WESUP_MAX_LEVELS, WESUP_E_ARG, "%s: n_levels=%d out of range", who, n_levels);
+    WESUP_REQUIRE(H > 0 && W > 0, WESUP_E_ARG, "%s: bad output size %dx%d", who, H, W);
+    WESUP_REQUIRE(layout == WESUP_CHW || layout == WESUP_HWC, WESUP_E_ARG, "%s: bad layout %d", who, layout);
+    L.n = n_levels; L.H = H; L.W = W;
+    int off = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        WESUP_REQUIRE(C[l] > 0 && h[l] > 0 && w[l] > 0, WESUP_E_ARG, "%s: level %d has empty shape", who, l);
+        if (layout == WESUP_HWC)
+            WESUP_REQUIRE(C[l] % 4 == 0, WESUP_E_ALIGN, "%s: HWC layout needs C[%d]=%d to be a multiple of 4", who, l, C[l]);
+        L.C[l] = C[l]; L.h[l] = h[l]; L.w[l] = w[l]; L.coff[l] = off;
+        L.sy[l] = bilinear_scale(h[l], H); L.sx[l] = bilinear_scale(w[l], W);
+        off += C[l];
+    }
+    L.Ctot = off;
+    return 0;
+}
+
+}  // namespace wesup
+
+using namespace wesup;
+
+extern "C" int wesup_hypercolumn_fwd(const void *const *side, const int *C, const int *h, const int *w, int n_levels,
+                                     int H, int W, void *out, int out_dtype, int layout, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WESUP_REQUIRE(side && out, WESUP_E_ARG, "wesup_hypercolumn_fwd: null pointer");
+    WESUP_REQUIRE(out_dtype == WESUP_F32 || out_dtype == WESUP_BF16, WESUP_E_ARG, "wesup_hypercolumn_fwd: bad dtype %d", out_dtype);
+    Levels L;
+    int rc = fill_levels(L, "wesup_hypercolumn_fwd", C, h, w, n_levels, H, W, layout);
+    if (rc) return rc;
+    for (int l = 0; l < n_levels; ++l) {
+        WESUP_REQUIRE(side[l] != nullptr, WESUP_E_ARG, "wesup_hypercolumn_fwd: side[%d] is null", l);
+        WESUP_REQUIRE(layout == WESUP_CHW || aligned16(side[l]), WESUP_E_ALIGN, "wesup_hypercolumn_fwd: side[%d] not 16-byte aligned", l);
+        L.src[l] = static_cast<const float *>(side[l]);
+        L.dst[l] = nullptr;
+    }
+    if (layout == WESUP_HWC) {
+        WESUP_REQUIRE(aligned16(out), WESUP_E_ALIGN, "wesup_hypercolumn_fwd: out not 16-byte aligned");
+        dim3 grid(cdiv(W, TILE_W), cdiv(H, TILE_H));
+        if (out_dtype == WESUP_F32) hyper_fwd_hwc_kernel<float><<<grid, 256, 0, stream>>>(L, (float *)out);
+        else hyper_fwd_hwc_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(L, (__nv_bfloat16 *)out);
+    } else {
+        int cmax = 0;
+        for (int l = 0; l < n_levels; ++l) cmax = cmax > C[l] ? cmax : C[l];
+        long per_level = (long)cmax * H * ((W + 3) / 4);
+        dim3 grid(cdiv(per_level, 256), 1, n_levels);
+        if (out_dtype == WESUP_F32) hyper_fwd_chw_kernel<float><<<grid, 256, 0, stream>>>(L, (float *)out);
+        else hyper_fwd_chw_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(L, (__nv_bfloat16 *)out);
+    }
+    WESUP_CHECK_LAUNCH("wesup_hypercolumn_fwd", 1);
+    return 0;
+}
+
+extern "C" int wesup_hypercolumn_bwd(const void *grad_out, int grad_dtype, int layout, const int *C, const int *h,
+                                     const int *w, int n_levels, int H, int W, void *const *grad_side, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WESUP_REQUIRE(grad_out && grad_side, WESUP_E_ARG, "wesup_hypercolumn_bwd: null pointer");
+    WESUP_REQUIRE(grad_dtype == WESUP_F32 || grad_dtype == WESUP_BF16, WESUP_E_ARG, "wesup_hypercolumn_bwd: bad dtype %d", grad_dtype);
+    Levels L;
+    int rc = fill_levels(L, "wesup_hypercolumn_bwd", C, h, w, n_levels, H, W, layout);
+    if (rc) return rc;
+    long biggest = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        WESUP_REQUIRE(grad_side[l] != nullptr, WESUP_E_ARG, "wesup_hypercolumn_bwd: grad_side[%d] is null", l);
+        WESUP_REQUIRE(layout == WESUP_CHW || aligned16(grad_side[l]), WESUP_E_ALIGN, "wesup_hypercolumn_bwd: grad_side[%d] not 16-byte aligned", l);
+        L.src[l] = nullptr;
+        L.dst[l] = static_cast<float *>(grad_side[l]);
+        long n = (long)h[l] * w[l] * (layout == WESUP_HWC ? C[l] / 4 : C[l]);
+        biggest = biggest > n ? biggest : n;
+    }
+    dim3 grid(cdiv(biggest, 256), n_levels);
+    if (layout == WESUP_HWC) {
+        WESUP_REQUIRE(aligned16(grad_out), WESUP_E_ALIGN, "wesup_hypercolumn_bwd: grad_out not 16-byte aligned");
+        if (grad_dtype == WESUP_F32) hyper_bwd_hwc_kernel<float><<<grid, 256, 0, stream>>>(L, (const float *)grad_out);
+        else hyper_bwd_hwc_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(L, (const __nv_bfloat16 *)grad_out);
+    } else {
+        if (grad_dtype == WESUP_F32) hyper_bwd_chw_kernel<float><<<grid, 256, 0, stream>>>(L, (const float *)grad_out);
+        else hyper_bwd_chw_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(L, (const __nv_bfloat16 *)grad_out);
+    }
+    WESUP_CHECK_LAUNCH("wesup_hypercolumn_bwd", 1);
+    return 0;
+}

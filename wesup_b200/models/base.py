@@ -1,0 +1,203 @@
+"""Trainer scaffolding with the reference's interface
+(/root/reference/models/base.py:16-360): `BaseConfig.to_dict`, and a
+`BaseTrainer` whose template methods (`preprocess`, `compute_loss`,
+`postprocess`, `post_epoch_hook`, `get_default_dataset/optimizer`) and loop
+(`train`, `train_one_epoch`, `train_one_iteration`, `evaluate`,
+`load/save_checkpoint`) behave the same way, so train.py-style drivers work
+unchanged.  The loop is host bookkeeping, not a kernel target; the one additive
+feature is data parallelism (`wesup_b200.parallel.GradientAllReduce`): when a
+process group is initialised, gradients are averaged over ranks between
+`backward()` and `optimizer.step()`.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import time
+from abc import ABC, abstractmethod
+from collections import defaultdict
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from ..utils import record, underline
+from ..utils.history import HistoryTracker
+
+
+class BaseConfig:
+    batch_size = 1
+    epochs = 10
+    epsilon = 1e-7
+
+    def to_dict(self):
+        return {name: getattr(self, name) for name in dir(self)
+                if not name.startswith("_") and name != "to_dict"}
+
+    def __str__(self):
+        return "\n".join(f"{k:<32s}{v}" for k, v in self.to_dict().items())
+
+
+class BaseTrainer(ABC):
+    def __init__(self, model, **kwargs):
+        self.device = kwargs.get("device", "cuda" if torch.cuda.is_available() else "cpu")
+        self.model = model.to(self.device)
+        self.kwargs = kwargs
+        self.logger = kwargs.get("logger")
+        if not self.logger:
+            self.logger = logging.getLogger("Train")
+            self.logger.setLevel(logging.DEBUG)
+            if not self.logger.handlers:
+                self.logger.addHandler(logging.StreamHandler())
+        self.initial_epoch = 1
+        self.record_dir = None
+        self.tracker = HistoryTracker()
+        self.dataloaders = None
+        self.optimizer, self.scheduler = None, None
+        self.metric_funcs = []
+        self.grad_sync = None            # set by enable_data_parallel()
+
+    # ---- template methods ---------------------------------------------------
+    @abstractmethod
+    def get_default_dataset(self, root_dir, train=True, proportion=1.0):
+        ...
+
+    def get_default_optimizer(self):
+        return torch.optim.SGD(self.model.parameters(), lr=1e-3), None
+
+    def preprocess(self, *data):
+        return [datum.to(self.device) for datum in data]
+
+    @abstractmethod
+    def compute_loss(self, pred, target, metrics=None):
+        ...
+
+    def postprocess(self, pred, target=None):
+        return pred if target is None else (pred, target)
+
+    def post_epoch_hook(self, epoch):
+        pass
+
+    # ---- data parallelism (additive) ---------------------------------------
+    def enable_data_parallel(self, process_group=None):
+        """Average gradients over the ranks of `process_group` every iteration."""
+        from ..parallel import GradientAllReduce
+        self.grad_sync = GradientAllReduce(self.model, process_group)
+        self.grad_sync.broadcast_parameters()
+        return self.grad_sync
+
+    # ---- checkpoints (key names are part of the surface) --------------------
+    def load_checkpoint(self, ckpt_path=None):
+        if ckpt_path is None:
+            self.record_dir = Path(record.prepare_record_dir())
+            return
+        self.record_dir = Path(ckpt_path).parent.parent
+        self.logger.info(f"Loading checkpoint from {ckpt_path}.")
+        ckpt = torch.load(ckpt_path, map_location=self.device)
+        self.initial_epoch = ckpt["epoch"] + 1
+        self.model.load_state_dict(ckpt["model_state_dict"])
+        if self.optimizer is not None and "optimizer_state_dict" in ckpt:
+            self.optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+        if self.scheduler is not None and "scheduler_state_dict" in ckpt:
+            self.scheduler.load_state_dict(ckpt["scheduler_state_dict"])
+
+    def save_checkpoint(self, ckpt_path, **extra):
+        ckpt = {"model_state_dict": self.model.state_dict(),
+                "optimizer_state_dict": self.optimizer.state_dict(), **extra}
+        if self.scheduler is not None:
+            ckpt["scheduler_state_dict"] = self.scheduler.state_dict()
+        torch.save(ckpt, ckpt_path)
+
+    # ---- the loop -------------------------------------------------------------
+    def train_one_iteration(self, phase, *data):
+        input_, target = self.preprocess(*data)
+        if self.grad_sync is not None:
+            self.grad_sync.zero_grad()       # keeps .grad as views of the flat all-reduce buffer
+        else:
+            self.optimizer.zero_grad()
+        metrics = {}
+        with torch.set_grad_enabled(phase == "train"):
+            pred = self.model(input_)
+            if phase == "train":
+                loss = self.compute_loss(pred, target, metrics=metrics)
+                if torch.isnan(loss):
+                    raise ValueError("Loss is nan!")
+                metrics["loss"] = loss.item()
+                loss.backward()
+                if self.grad_sync is not None:
+                    self.grad_sync.average_gradients()
+                self.optimizer.step()
+        pred, target = self.postprocess(pred, target)
+        self.tracker.step({**metrics, **self.evaluate(pred, target)})
+
+    def train_one_epoch(self, no_val=False):
+        for phase in (["train"] if no_val else ["train", "val"]):
+            self.logger.info(f"{phase.capitalize()} phase:")
+            start = time.time()
+            if phase == "train":
+                self.model.train()
+                self.tracker.train()
+            else:
+                self.model.eval()
+                self.tracker.eval()
+            for data in self.dataloaders[phase]:
+                try:
+                    self.train_one_iteration(phase, *data)
+                except RuntimeError as ex:       # same policy as the reference (base.py:234-237)
+                    self.logger.exception(ex)
+            self.logger.info(f"Took {time.time() - start:.2f}s.")
+            self.logger.info(self.tracker.log())
+
+    def train(self, data_root, **kwargs):
+        self.kwargs = {**self.kwargs, **kwargs}
+        self.optimizer, self.scheduler = self.get_default_optimizer()
+        self.load_checkpoint(self.kwargs.get("checkpoint"))
+        self.logger.addHandler(logging.FileHandler(self.record_dir / "train.log"))
+        plain = {k: v for k, v in self.kwargs.items() if isinstance(v, (int, float, str, tuple))}
+        record.save_params(self.record_dir, plain)
+        self.logger.info(str(plain) + "\n")
+        self.tracker.save_path = self.record_dir / "history.csv"
+        data_root = Path(data_root)
+        train_path, val_path = data_root / "train", data_root / "val"
+        train_dataset = self.get_default_dataset(train_path, proportion=self.kwargs.get("proportion", 1))
+        if hasattr(train_dataset, "summary"):
+            train_dataset.summary(logger=self.logger)
+        workers = self.kwargs.get("num_workers", os.cpu_count())
+        sampler = None
+        if self.grad_sync is not None:
+            sampler = torch.utils.data.distributed.DistributedSampler(
+                train_dataset, num_replicas=self.grad_sync.world_size, rank=self.grad_sync.rank, shuffle=True)
+        self.dataloaders = {"train": torch.utils.data.DataLoader(
+            train_dataset, batch_size=self.kwargs.get("batch_size"), shuffle=sampler is None,
+            sampler=sampler, num_workers=workers)}
+        if val_path.exists():
+            val_dataset = self.get_default_dataset(val_path, train=False)
+            self.dataloaders["val"] = torch.utils.data.DataLoader(val_dataset, batch_size=1, num_workers=workers)
+        self.logger.info(underline("\nTraining Stage", "="))
+        self.metric_funcs = self.kwargs.get("metrics") or []
+        total_epochs = self.kwargs.get("epochs") + self.initial_epoch - 1
+        for epoch in range(self.initial_epoch, total_epochs + 1):
+            self.logger.info(underline(f"\nEpoch {epoch}/{total_epochs}", "-"))
+            if sampler is not None:
+                sampler.set_epoch(epoch)
+            self.tracker.start_new_epoch(self.optimizer.param_groups[0]["lr"])
+            self.train_one_epoch(no_val=not val_path.exists())
+            self.post_epoch_hook(epoch)
+            if self.grad_sync is None or self.grad_sync.rank == 0:
+                self.tracker.save()
+                ckpt_dir = self.record_dir / "checkpoints"
+                ckpt_dir.mkdir(exist_ok=True)
+                self.save_checkpoint(ckpt_dir / f"ckpt.{epoch:04d}.pth", epoch=epoch)
+                for old in sorted(ckpt_dir.glob("*.pth"))[:-1]:
+                    os.remove(old)
+        if self.grad_sync is None or self.grad_sync.rank == 0:
+            self.logger.info(self.tracker.report())
+
+    def evaluate(self, pred, target=None, verbose=False):
+        if target is None:
+            return {}
+        scores = defaultdict(list)
+        for P, G in zip(pred, target):
+            for func in self.metric_funcs:
+                scores[func.__name__].append(func(P, G))
+        return {k: np.mean(v) for k, v in scores.items()}

@@ -1,0 +1,300 @@
+"""B200-native mirror of the reference's `models/wesup.py`.
+
+Same public surface (/root/reference/models/wesup.py): `WESUPConfig`, `WESUP`
+(`forward((x, sp_maps))`, attributes `sp_features` / `sp_pred` / `feature_maps`,
+identical `state_dict` keys), `WESUPPixelInference`, `WESUPTrainer`
+(`preprocess` / `compute_loss` / `postprocess` / ...), and the module-level
+`_preprocess_superpixels`, `_cross_entropy`, `_label_propagate`.  Underneath,
+the superpixel stage runs on the hand-written CUDA kernels behind the C ABI
+(`wesup_b200.ops`); VGG16 convolutions and the small MLP stay on
+PyTorch/cuDNN/cuBLAS as in the reference.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import os.path as osp
+import warnings
+from functools import partial
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..ops import SuperpixelMaps
+from ..utils import empty_tensor, is_empty_tensor
+from .base import BaseConfig, BaseTrainer
+
+# torchvision's vgg16().features layout (reference: models/wesup.py:199); built
+# here so that checkpoint keys are `backbone.{0,2,5,...}.{weight,bias}`.
+_VGG16 = (64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M")
+
+
+def _vgg16_features(pretrained: bool) -> nn.Sequential:
+    layers, cin = [], 3
+    for item in _VGG16:
+        if item == "M":
+            layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
+        else:
+            layers += [nn.Conv2d(cin, item, kernel_size=3, padding=1), nn.ReLU(inplace=True)]
+            cin = item
+    features = nn.Sequential(*layers)
+    if pretrained:
+        try:            # ImageNet weights as in the reference; offline boxes fall back to random init
+            from torchvision import models as tvm
+            features.load_state_dict(tvm.vgg16(weights=tvm.VGG16_Weights.IMAGENET1K_V1).features.state_dict())
+        except Exception as ex:  # noqa: BLE001  (URLError / OSError / missing torchvision)
+            warnings.warn(f"VGG16 ImageNet weights unavailable ({type(ex).__name__}); using random init")
+    return features
+
+
+# ---------------------------------------------------------------------------
+# module-level functions (reference: models/wesup.py:18-139)
+# ---------------------------------------------------------------------------
+def _preprocess_superpixels(segments, mask=None, epsilon=1e-7, dense=False, n_sp=None):
+    """Superpixel rows + labels from a SLIC label map (reference :18-63).
+
+    Returns `(sp_maps, sp_labels)`.  `sp_maps` is a compact `SuperpixelMaps`
+    (label map + counts + CSR) instead of the dense `(N,H,W)` tensor; pass
+    `dense=True` for the reference tensor.  Row order, the labeled/unlabeled
+    split and the multi-hot quantisation are bit-identical to the reference.
+    `epsilon` only guards a division whose result is compared with zero / with
+    the row maximum in the reference, so integer class counts are equivalent.
+    """
+    if mask is not None and is_empty_tensor(mask):
+        mask = None
+    sp = SuperpixelMaps.from_labels(segments, mask, n_sp=n_sp)
+    sp_labels = sp.sp_labels if mask is not None else empty_tensor().to(segments.device)
+    return (sp.to_dense() if dense else sp), sp_labels
+
+
+def _cross_entropy(y_hat, y_true, class_weights=None, epsilon=1e-7):
+    """Semi-supervised cross entropy (reference :66-96).  Rows whose label is
+    all-zero are ignored; multi-hot rows count once in the denominator.  Unlike
+    the reference this never syncs with the host: with no labeled row the
+    numerator is exactly zero, so dividing by max(count, 1) returns the same 0."""
+    y_hat = torch.clamp(y_hat, min=epsilon, max=1 - epsilon)
+    labeled = (y_true.sum(dim=1) > 0).sum().float()
+    ce = -y_true * torch.log(y_hat)
+    if class_weights is not None:
+        ce = ce * class_weights.unsqueeze(0).float()
+    return ce.sum() / torch.clamp(labeled, min=1.0)
+
+
+def _label_propagate(features, y_l, threshold=0.95):
+    """Nearest-labeled-neighbour label propagation (reference :99-139) as one
+    fused kernel; returns the (n_u, C) pseudo-label matrix."""
+    return ops.label_propagate(features, y_l, threshold)
+
+
+class WESUPConfig(BaseConfig):
+    """Field-for-field the reference's configuration (models/wesup.py:142-179)."""
+    rescale_factor = 0.5
+    multiscale_range = (0.3, 0.4)
+    n_classes = 2
+    class_weights = (3, 1)          # never applied by the reference either (:434)
+    sp_area = 200
+    sp_compactness = 40
+    enable_propagation = True
+    propagate_threshold = 0.8
+    propagate_weight = 0.5
+    momentum = 0.9
+    weight_decay = 0.001
+    freeze_backbone = False
+    batch_size = 1
+    epochs = 300
+
+
+class WESUP(nn.Module):
+    """Reference: models/wesup.py:182-304.
+
+    Extra keyword arguments (all optional, none stored in the state_dict):
+      pretrained    load ImageNet VGG16 weights when reachable (default True)
+      hc_dtype      torch.float32 (default) or torch.bfloat16 hypercolumn storage
+      hc_layout     'hwc' (default, pixel-major) or 'chw' (the reference's layout)
+    """
+
+    def __init__(self, n_classes=2, D=32, **kwargs):
+        super().__init__()
+        self.kwargs = kwargs
+        self.backbone = _vgg16_features(kwargs.get("pretrained", True))
+        self.fm_channels_sum = 0
+        self._side_names = []
+        for layer in self.backbone:
+            if isinstance(layer, nn.Conv2d):
+                name = f"side_conv{self.fm_channels_sum}"
+                setattr(self, name, nn.Conv2d(layer.out_channels, layer.out_channels // 2, 1))
+                self._side_names.append(name)
+                self.fm_channels_sum += layer.out_channels // 2
+        self.fc_layers = nn.Sequential(
+            nn.Linear(self.fm_channels_sum, 1024), nn.ReLU(),
+            nn.Linear(1024, 1024), nn.ReLU(),
+            nn.Linear(1024, D), nn.ReLU())
+        self.classifier = nn.Sequential(
+            nn.Linear(D, self.kwargs.get("n_classes", n_classes)), nn.Softmax(dim=1))
+        self.hc_dtype = kwargs.get("hc_dtype", torch.float32)
+        self.hc_layout = kwargs.get("hc_layout", "hwc")
+        self.feature_maps = None
+        self.fm_size = None
+        self.sp_features = None
+        self.sp_pred = None
+
+    # -- backbone + 1x1 side convs (cuDNN; the reported baseline) --------------
+    def _side_outputs(self, x):
+        """Side conv on every PRE-ReLU conv output (the reference hooks the Conv2d
+        modules, :205-210,253).  Runs channels_last so the side outputs are already
+        pixel-major in memory for the hypercolumn kernel."""
+        if self.hc_layout == "hwc":
+            x = x.contiguous(memory_format=torch.channels_last)
+        sides, names = [], iter(self._side_names)
+        for layer in self.backbone:
+            if isinstance(layer, nn.Conv2d):
+                x = layer(x)
+                sides.append(getattr(self, next(names))(x))
+            elif isinstance(layer, nn.ReLU):
+                x = F.relu(x)            # out of place: the side conv saved the pre-ReLU tensor
+            else:
+                x = layer(x)
+        return sides
+
+    def _hypercolumn(self, x):
+        self.fm_size = (x.size(2), x.size(3))
+        feats = ops.hypercolumn(self._side_outputs(x), self.fm_size, dtype=self.hc_dtype, layout=self.hc_layout)
+        # same attribute as the reference, exposed in its (C,H,W) shape without a copy
+        self.feature_maps = feats if self.hc_layout == "chw" else feats.t().view(-1, *self.fm_size)
+        return feats
+
+    def forward(self, x):
+        """x = (image (1,3,H,W), sp_maps); returns class-1 probability (1,H,W)."""
+        x, sp_maps = x
+        sp = sp_maps if isinstance(sp_maps, SuperpixelMaps) else SuperpixelMaps.from_dense(sp_maps)
+        feats = self._hypercolumn(x)
+        pooled = ops.sp_pool(feats, sp, layout=self.hc_layout)
+        x = self.fc_layers(pooled)
+        self.sp_features = x
+        self.sp_pred = self.classifier(x)
+        return ops.paint(sp, self.sp_pred, cls=1)
+
+
+class WESUPPixelInference(WESUP):
+    """Pixel-wise inference (reference: models/wesup.py:307-400): the hypercolumn
+    goes straight through the MLP, one row per pixel.  Loads the same
+    state_dict as `WESUP`.  The pixel-major hypercolumn is already the
+    (H*W, 2112) operand the first Linear wants, so the reference's `x.t()`
+    (:398) disappears."""
+
+    def __init__(self, n_classes=2, D=32, **kwargs):
+        kwargs = {**kwargs, "hc_layout": "hwc"}
+        super().__init__(n_classes=n_classes, D=D, **kwargs)
+
+    def forward(self, x):
+        height, width = x.size()[-2:]
+        feats = self._hypercolumn(x)
+        if feats.dtype != torch.float32:
+            feats = feats.float()
+        out = self.classifier(self.fc_layers(feats))
+        return out.view(height, width, -1)
+
+
+class WESUPTrainer(BaseTrainer):
+    """Reference: models/wesup.py:403-547."""
+
+    def __init__(self, model, **kwargs):
+        config = WESUPConfig()
+        if config.freeze_backbone:
+            for param in model.backbone.parameters():
+                param.requires_grad = False
+        kwargs = {**config.to_dict(), **kwargs}
+        super().__init__(model, **kwargs)
+        self.xentropy = partial(_cross_entropy)
+
+    def get_default_dataset(self, root_dir, train=True, proportion=1.0):
+        # PNG/CSV readers and albumentations augmentation are CPU I/O outside this
+        # path; plug the reference's utils.data in.
+        try:
+            from utils.data import Digest2019PointDataset, SegmentationDataset  # the reference's, if on sys.path
+        except ImportError as ex:
+            raise RuntimeError("datasets come from the reference's utils/data.py; put it on sys.path "
+                               "(see INTEGRATION.md)") from ex
+        if train:
+            if osp.exists(osp.join(root_dir, "points")):
+                return Digest2019PointDataset(root_dir, proportion=proportion,
+                                              multiscale_range=self.kwargs.get("multiscale_range"))
+            return SegmentationDataset(root_dir, proportion=proportion,
+                                       multiscale_range=self.kwargs.get("multiscale_range"))
+        return SegmentationDataset(root_dir, rescale_factor=self.kwargs.get("rescale_factor"), train=False)
+
+    def get_default_optimizer(self):
+        optimizer = torch.optim.SGD(
+            filter(lambda p: p.requires_grad, self.model.parameters()),
+            lr=5e-5, momentum=self.kwargs.get("momentum"), weight_decay=self.kwargs.get("weight_decay"))
+        return optimizer, None      # the reference builds a scheduler and discards it (:452-455)
+
+    def segment(self, img):
+        """GPU SLIC with the reference's parameters (:471-476).  Returns the int32
+        label map and the number of labels (one host sync, like the reference's
+        `.cpu()` round trip but without moving the image)."""
+        n_segments = int(img.size(-2) * img.size(-1) / self.kwargs.get("sp_area"))
+        labels, n_labels = ops.slic(img, n_segments=n_segments, compactness=self.kwargs.get("sp_compactness"))
+        return labels, int(n_labels.item())
+
+    def preprocess(self, *data):
+        data = [datum.to(self.device, non_blocking=True) for datum in data]
+        if len(data) == 3:
+            img, pixel_mask, point_mask = data
+        elif len(data) == 2:
+            img, pixel_mask = data
+            point_mask = empty_tensor()
+        elif len(data) == 1:
+            img, = data
+            point_mask = empty_tensor()
+            pixel_mask = empty_tensor()
+        else:
+            raise ValueError("Invalid input data for WESUP")
+        segments, n_sp = self.segment(img)
+        if point_mask is not None and not is_empty_tensor(point_mask):
+            mask = point_mask.squeeze(0) if point_mask.dim() == 4 else point_mask.squeeze()
+        elif pixel_mask is not None and not is_empty_tensor(pixel_mask):
+            mask = pixel_mask.squeeze(0) if pixel_mask.dim() == 4 else pixel_mask.squeeze()
+        else:
+            mask = None
+        sp_maps, sp_labels = _preprocess_superpixels(segments, mask, epsilon=self.kwargs.get("epsilon"), n_sp=n_sp)
+        return (img, sp_maps), (pixel_mask, sp_labels)
+
+    def compute_loss(self, pred, target, metrics=None):
+        _, sp_labels = target
+        sp_features = self.model.sp_features
+        sp_pred = self.model.sp_pred
+        if sp_pred is None:
+            raise RuntimeError("You must run a forward pass before computing loss.")
+        total_num = sp_pred.size(0)
+        labeled_num = sp_labels.size(0)
+        if labeled_num < total_num:          # weakly-supervised mode
+            loss = self.xentropy(sp_pred[:labeled_num], sp_labels)
+            if self.kwargs.get("enable_propagation"):
+                propagated_labels = _label_propagate(sp_features, sp_labels,
+                                                     threshold=self.kwargs.get("propagate_threshold"))
+                propagate_loss = self.xentropy(sp_pred[labeled_num:], propagated_labels)
+                loss = loss + self.kwargs.get("propagate_weight") * propagate_loss
+            if metrics is not None and isinstance(metrics, dict):
+                metrics["labeled_sp_ratio"] = labeled_num / total_num
+                if self.kwargs.get("enable_propagation"):
+                    metrics["propagated_labels"] = propagated_labels.sum().item()
+                    metrics["propagate_loss"] = propagate_loss.item()
+        else:                                # fully-supervised mode
+            loss = self.xentropy(sp_pred, sp_labels)
+        self.model.sp_pred = None            # clear outdated prediction (:529)
+        return loss
+
+    def postprocess(self, pred, target=None):
+        pred = pred.round().long()
+        if target is not None:
+            return pred, target[0].argmax(dim=1)
+        return pred
+
+    def post_epoch_hook(self, epoch):
+        if self.scheduler is not None:
+            labeled_loss = np.mean(self.tracker.history["loss"])
+            if "propagate_loss" in self.tracker.history:
+                labeled_loss -= np.mean(self.tracker.history["propagate_loss"])
+            self.scheduler.step(labeled_loss)

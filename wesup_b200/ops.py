@@ -1,0 +1,311 @@
+"""Torch-facing operators of the superpixel stage.
+
+Each function/autograd.Function here is a thin shim over one C-ABI entry point
+of libwesup_b200.so (include/wesup_b200.h): it allocates outputs and workspaces
+with torch's caching allocator, passes raw device pointers plus the current
+CUDA stream, and turns non-zero return codes into RuntimeError.  No math
+happens in Python and there is no fallback path: CPU tensors are rejected.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BF16, CHW, F32, HWC, check
+
+_DTYPES = {torch.float32: F32, torch.bfloat16: BF16}
+_LAYOUTS = {"chw": CHW, "hwc": HWC}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"wesup_b200: `{name}` must be a CUDA tensor (the superpixel stage has no CPU path)")
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ---------------------------------------------------------------------------
+# compact superpixel representation (replaces the dense (N,H,W) sp_maps)
+# ---------------------------------------------------------------------------
+class SuperpixelMaps:
+    """What `preprocess` hands to `WESUP.forward` in place of the reference's dense
+    `sp_maps (N,H,W)` (/root/reference/models/wesup.py:57-61): the relabelled int32
+    label map plus per-row counts and a CSR of pixel ids.  Row k of every
+    downstream tensor (pooled features, sp_features, sp_pred, y_u) refers to
+    original superpixel `order[k]`, exactly as row k of the dense maps did.
+
+    Quacks enough like the dense tensor for the reference's call sites:
+    `.size()`, `.shape`, `.dim()`, `.device`, `.to()`; `.to_dense()` rebuilds the
+    reference tensor (tests / legacy callers only)."""
+
+    def __init__(self, height, width, n, order, row_labels, counts, seg_offsets, seg_pixels,
+                 sp_labels=None, n_labeled_dev=None):
+        self.height, self.width, self.n = int(height), int(width), int(n)
+        self.order, self.row_labels, self.counts = order, row_labels, counts
+        self.seg_offsets, self.seg_pixels = seg_offsets, seg_pixels
+        self.sp_labels_full = sp_labels            # (n, n_cls) incl. zero rows, or None
+        self._n_labeled_dev = n_labeled_dev
+        self._n_labeled: Optional[int] = None
+
+    # -- tensor-like surface -------------------------------------------------
+    def size(self, dim: Optional[int] = None):
+        s = torch.Size((self.n, self.height, self.width))
+        return s if dim is None else s[dim]
+
+    @property
+    def shape(self):
+        return self.size()
+
+    def dim(self) -> int:
+        return 3
+
+    @property
+    def device(self):
+        return self.row_labels.device
+
+    def to(self, *args, **kwargs):
+        dev = torch.device(args[0]) if args and not isinstance(args[0], torch.dtype) else kwargs.get("device")
+        if dev is None or dev == self.device:
+            return self
+        raise RuntimeError("SuperpixelMaps lives on the GPU that built it")
+
+    @property
+    def n_labeled(self) -> int:
+        """Host copy of the labeled-row count (one D2H sync, cached)."""
+        if self._n_labeled is None:
+            self._n_labeled = 0 if self._n_labeled_dev is None else int(self._n_labeled_dev.item())
+        return self._n_labeled
+
+    @property
+    def sp_labels(self) -> Optional[torch.Tensor]:
+        if self.sp_labels_full is None:
+            return None
+        return self.sp_labels_full[: self.n_labeled]
+
+    @property
+    def label_map(self) -> torch.Tensor:
+        return self.row_labels.view(self.height, self.width)
+
+    def to_dense(self) -> torch.Tensor:
+        rows = torch.arange(self.n, device=self.device, dtype=torch.int32).view(-1, 1, 1)
+        maps = (self.label_map.unsqueeze(0) == rows).float()
+        return maps / maps.sum(dim=(1, 2), keepdim=True)
+
+    # -- constructors ----------------------------------------------------------
+    @staticmethod
+    def from_labels(labels: torch.Tensor, mask: Optional[torch.Tensor] = None, n_sp: Optional[int] = None) -> "SuperpixelMaps":
+        """labels: (H,W) integer ids in [0,n_sp); mask: (C,H,W) int64 one-hot-or-zero or None."""
+        _require_cuda(labels, "segments")
+        if labels.dim() != 2:
+            raise ValueError("segments must be (H, W)")
+        h, w = labels.shape
+        lab32 = labels.to(torch.int32).contiguous()
+        if n_sp is None:
+            n_sp = int(lab32.max().item()) + 1          # the reference does the same sync (models/wesup.py:41)
+        dev = labels.device
+        n_cls = 0
+        mask64 = None
+        if mask is not None and mask.dim() != 0:
+            if mask.dim() != 3 or mask.shape[1:] != labels.shape:
+                raise ValueError("mask must be (C, H, W) matching segments")
+            mask64 = mask.to(device=dev, dtype=torch.int64).contiguous()
+            n_cls = mask64.size(0)
+        i32 = dict(dtype=torch.int32, device=dev)
+        order = torch.empty(n_sp, **i32)
+        row_labels = torch.empty(h * w, **i32)
+        counts = torch.empty(n_sp, **i32)
+        seg_offsets = torch.empty(n_sp + 1, **i32)
+        seg_pixels = torch.empty(h * w, **i32)
+        n_labeled = torch.zeros(1, **i32)
+        sp_labels = torch.empty(n_sp, n_cls, dtype=torch.float32, device=dev) if n_cls else None
+        lib = _lib.load()
+        ws = _ws(lib.wesup_sp_stats_workspace_bytes(h, w, n_sp, n_cls), dev)
+        check(lib.wesup_sp_stats(lab32.data_ptr(), mask64.data_ptr() if mask64 is not None else None, h, w, n_cls, n_sp,
+                                 order.data_ptr(), row_labels.data_ptr(), counts.data_ptr(), seg_offsets.data_ptr(),
+                                 seg_pixels.data_ptr(), sp_labels.data_ptr() if sp_labels is not None else None,
+                                 n_labeled.data_ptr(), ws.data_ptr(), _stream()), "wesup_sp_stats")
+        return SuperpixelMaps(h, w, n_sp, order, row_labels, counts, seg_offsets, seg_pixels, sp_labels,
+                              n_labeled if n_cls else None)
+
+    @staticmethod
+    def from_dense(sp_maps: torch.Tensor) -> "SuperpixelMaps":
+        """Legacy callers that still pass the dense (N,H,W) tensor: the owner of a
+        pixel is argmax over rows, as at /root/reference/models/wesup.py:295."""
+        _require_cuda(sp_maps, "sp_maps")
+        owner = sp_maps.argmax(dim=0)
+        return SuperpixelMaps.from_labels(owner, None, n_sp=sp_maps.size(0))
+
+
+# ---------------------------------------------------------------------------
+# (a) hypercolumn
+# ---------------------------------------------------------------------------
+def _as_hwc(t: torch.Tensor) -> torch.Tensor:
+    """(1,C,h,w) -> memory (h,w,C); free for channels_last tensors."""
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+class _Hypercolumn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, size, dtype, layout, *sides):
+        lib = _lib.load()
+        H, W = size
+        for s in sides:
+            _require_cuda(s, "side output")
+            if s.dim() != 4 or s.size(0) != 1 or s.dtype != torch.float32:
+                raise ValueError("side outputs must be fp32 (1,C,h,w)")
+        C = [s.size(1) for s in sides]
+        h = [s.size(2) for s in sides]
+        w = [s.size(3) for s in sides]
+        mem = [_as_hwc(s) if layout == HWC else s.contiguous() for s in sides]
+        ctot = sum(C)
+        dev = sides[0].device
+        out = torch.empty((H * W, ctot) if layout == HWC else (ctot, H, W), dtype=dtype, device=dev)
+        check(lib.wesup_hypercolumn_fwd(_lib.ptr_array([m.data_ptr() for m in mem]), _lib.int_array(C), _lib.int_array(h),
+                                        _lib.int_array(w), len(sides), H, W, out.data_ptr(), _DTYPES[dtype], layout,
+                                        _stream()), "wesup_hypercolumn_fwd")
+        ctx.geom = (C, h, w, H, W, layout)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        C, h, w, H, W, layout = ctx.geom
+        grad_out = grad_out.contiguous()
+        dev = grad_out.device
+        if layout == HWC:
+            mem = [torch.empty((1, hh, ww, cc), dtype=torch.float32, device=dev) for cc, hh, ww in zip(C, h, w)]
+        else:
+            mem = [torch.empty((1, cc, hh, ww), dtype=torch.float32, device=dev) for cc, hh, ww in zip(C, h, w)]
+        check(lib.wesup_hypercolumn_bwd(grad_out.data_ptr(), _DTYPES[grad_out.dtype], layout, _lib.int_array(C),
+                                        _lib.int_array(h), _lib.int_array(w), len(C), H, W,
+                                        _lib.ptr_array([m.data_ptr() for m in mem]), _stream()), "wesup_hypercolumn_bwd")
+        grads = [m.permute(0, 3, 1, 2) if layout == HWC else m for m in mem]
+        return (None, None, None, *grads)
+
+
+def hypercolumn(sides: Sequence[torch.Tensor], size: Tuple[int, int], dtype=torch.float32, layout: str = "hwc") -> torch.Tensor:
+    """Fused bilinear(align_corners=True) upsample + channel concat of the side
+    outputs (/root/reference/models/wesup.py:254-261).  Returns (H*W, C) for
+    layout 'hwc' or (C, H, W) for 'chw'."""
+    return _Hypercolumn.apply((int(size[0]), int(size[1])), dtype, _LAYOUTS[layout], *sides)
+
+
+# ---------------------------------------------------------------------------
+# (b) pooling
+# ---------------------------------------------------------------------------
+class _SpPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, sp: SuperpixelMaps, layout):
+        lib = _lib.load()
+        _require_cuda(feat, "features")
+        feat = feat.contiguous()
+        hw = sp.height * sp.width
+        if layout == HWC:
+            if feat.dim() != 2 or feat.size(0) != hw:
+                raise ValueError(f"features must be (H*W={hw}, C) for the hwc layout, got {tuple(feat.shape)}")
+            c = feat.size(1)
+        else:
+            if feat.dim() != 3 or feat.size(1) * feat.size(2) != hw:
+                raise ValueError(f"features must be (C, H, W) for the chw layout, got {tuple(feat.shape)}")
+            c = feat.size(0)
+        pooled = torch.empty((sp.n, c), dtype=torch.float32, device=feat.device)
+        check(lib.wesup_sp_pool_fwd(feat.data_ptr(), _DTYPES[feat.dtype], layout, sp.seg_offsets.data_ptr(),
+                                    sp.seg_pixels.data_ptr(), hw, c, sp.n, pooled.data_ptr(), _stream()), "wesup_sp_pool_fwd")
+        ctx.sp, ctx.layout, ctx.meta = sp, layout, (feat.shape, feat.dtype, c)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, grad_pooled):
+        lib = _lib.load()
+        sp = ctx.sp
+        shape, dtype, c = ctx.meta
+        grad_pooled = grad_pooled.contiguous().float()
+        grad_feat = torch.empty(shape, dtype=dtype, device=grad_pooled.device)
+        check(lib.wesup_sp_pool_bwd(grad_pooled.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
+                                    sp.height * sp.width, c, sp.n, grad_feat.data_ptr(), _DTYPES[dtype], ctx.layout,
+                                    _stream()), "wesup_sp_pool_bwd")
+        return grad_feat, None, None
+
+
+def sp_pool(feat: torch.Tensor, sp: SuperpixelMaps, layout: str = "hwc") -> torch.Tensor:
+    """Per-superpixel mean of the pixel features -> (N, C) fp32; replaces
+    torch.mm(sp_maps, x.t()) (/root/reference/models/wesup.py:284-285)."""
+    return _SpPool.apply(feat, sp, _LAYOUTS[layout])
+
+
+def paint(sp: SuperpixelMaps, sp_pred: torch.Tensor, cls: int = 1) -> torch.Tensor:
+    """pred[p] = sp_pred[row(p), cls] -> (1,H,W); replaces the argmax + per-superpixel
+    index_put loop (/root/reference/models/wesup.py:295-304)."""
+    lib = _lib.load()
+    sp_pred = sp_pred.detach().contiguous().float()
+    _require_cuda(sp_pred, "sp_pred")
+    out = torch.empty((1, sp.height, sp.width), dtype=torch.float32, device=sp_pred.device)
+    check(lib.wesup_sp_paint(sp.row_labels.data_ptr(), sp_pred.data_ptr(), sp.height * sp.width, sp_pred.size(1), cls,
+                             out.data_ptr(), _stream()), "wesup_sp_paint")
+    return out
+
+
+# ---------------------------------------------------------------------------
+# (c) label propagation
+# ---------------------------------------------------------------------------
+def label_propagate(features: torch.Tensor, y_l: torch.Tensor, threshold: float = 0.95, return_aux: bool = False):
+    """Fused distance -> similarity -> arg-max -> threshold -> label copy
+    (/root/reference/models/wesup.py:99-139).  Returns y_u (n_u, C) [, src, max_sim]."""
+    lib = _lib.load()
+    features = features.detach().contiguous().float()
+    y_l = y_l.detach().contiguous().float()
+    _require_cuda(features, "features")
+    n, d = features.shape
+    n_l, n_cls = y_l.shape
+    n_u = n - n_l
+    dev = features.device
+    y_u = torch.zeros((n_u, n_cls), dtype=torch.float32, device=dev)
+    src = torch.zeros(n_u, dtype=torch.int32, device=dev)
+    sim = torch.zeros(n_u, dtype=torch.float32, device=dev)
+    if n_u > 0 and n_l > 0:
+        ws = _ws(lib.wesup_label_propagate_workspace_bytes(n, d, n_l), dev)
+        check(lib.wesup_label_propagate(features.data_ptr(), n, d, n_l, y_l.data_ptr(), n_cls, float(threshold),
+                                        y_u.data_ptr(), src.data_ptr(), sim.data_ptr(), ws.data_ptr(), _stream()),
+              "wesup_label_propagate")
+    if return_aux:
+        return y_u, src, sim
+    return y_u
+
+
+# ---------------------------------------------------------------------------
+# (d) SLIC
+# ---------------------------------------------------------------------------
+def slic(img: torch.Tensor, n_segments: int, compactness: float = 10.0, max_iter: int = 10,
+         enforce_connectivity: bool = True):
+    """GPU SLIC with scikit-image's semantics (/root/reference/models/wesup.py:471-476).
+    img: (3,H,W) or (1,3,H,W) fp32 in [0,1] on the GPU.  Returns (labels int32 (H,W),
+    n_labels int32 device scalar tensor of shape (1,))."""
+    lib = _lib.load()
+    _require_cuda(img, "img")
+    if img.dim() == 4:
+        if img.size(0) != 1:
+            raise ValueError("SLIC takes one image at a time (the reference is batch-1)")
+        img = img[0]
+    if img.dim() != 3 or img.size(0) != 3:
+        raise ValueError("img must be (3,H,W)")
+    img = img.contiguous().float()
+    _, h, w = img.shape
+    nbytes = lib.wesup_slic_workspace_bytes(h, w, int(n_segments))
+    if nbytes == 0:
+        raise ValueError(f"degenerate SLIC configuration: {h}x{w} image, n_segments={n_segments}")
+    dev = img.device
+    ws = _ws(nbytes, dev)
+    labels = torch.empty((h, w), dtype=torch.int32, device=dev)
+    n_labels = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib.wesup_slic(img.data_ptr(), CHW, h, w, int(n_segments), float(compactness), int(max_iter),
+                         int(bool(enforce_connectivity)), labels.data_ptr(), n_labels.data_ptr(), ws.data_ptr(), _stream()),
+          "wesup_slic")
+    return labels, n_labels

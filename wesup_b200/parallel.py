@@ -1,0 +1,111 @@
+"""Data parallelism for the two places the path shards:
+image batches for training (one exchange step: gradient all-reduce over
+NCCL/NVLink) and tiles for tiled inference (no data-path collective, only a
+gather of finished tiles).  One process per GPU, `torch.distributed` plumbing.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str | None = None):
+    """Initialise the default process group from torchrun's environment.
+    Returns (rank, world_size, local_rank); a no-op single-process answer when
+    WORLD_SIZE is unset or 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        kwargs = {}
+        if backend == "nccl":
+            kwargs["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
+    return rank, world, local
+
+
+class GradientAllReduce:
+    """Gradient averaging over ranks with ONE collective per step.
+
+    All parameter gradients live as views into a single flat fp32 buffer
+    (18.87 M parameters = 75.5 MB for WESUP), so `average_gradients()` is a
+    single in-place all-reduce of that buffer followed by a scale -- no
+    per-parameter launches, no copies.  Every parameter receives a gradient
+    every step on this path, so no unused-parameter
+    handling is needed."""
+
+    def __init__(self, model: torch.nn.Module, process_group=None):
+        self.group = process_group
+        self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        self.model = model
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        offset = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[offset:offset + n].view_as(p)
+            offset += n
+
+    def zero_grad(self):
+        """Use instead of optimizer.zero_grad(set_to_none=True), which would drop the views."""
+        self.flat.zero_()
+
+    def _rebind(self):
+        offset = 0
+        for p in self.params:
+            n = p.numel()
+            view = self.flat[offset:offset + n].view_as(p)
+            if p.grad is None:
+                view.zero_()
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+            offset += n
+
+    def average_gradients(self):
+        self._rebind()
+        if self.world_size > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.div_(self.world_size)
+
+    def broadcast_parameters(self, src: int = 0):
+        if self.world_size > 1:
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t.data, src=src, group=self.group)
+
+
+def shard_range(n_items: int, rank: int, world_size: int):
+    """Contiguous block partition: rank r owns [lo, hi).  Blocks differ by at most
+    one item; contiguous so each rank's tiles form a stripe of the slide."""
+    base, extra = divmod(n_items, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_tiles(local_tiles: torch.Tensor, n_total: int, rank: int, world_size: int, group=None):
+    """Gather per-rank stacks of finished tiles (n_local, ...) to rank 0 in tile
+    order.  Returns the (n_total, ...) stack on rank 0 and None elsewhere."""
+    if world_size == 1:
+        return local_tiles
+    counts = [shard_range(n_total, r, world_size) for r in range(world_size)]
+    biggest = max(hi - lo for lo, hi in counts)
+    pad = torch.zeros((biggest, *local_tiles.shape[1:]), dtype=local_tiles.dtype, device=local_tiles.device)
+    pad[: local_tiles.size(0)] = local_tiles
+    bufs = [torch.empty_like(pad) for _ in range(world_size)] if rank == 0 else None
+    dist.gather(pad, bufs, dst=0, group=group)
+    if rank != 0:
+        return None
+    return torch.cat([bufs[r][: hi - lo] for r, (lo, hi) in enumerate(counts)], dim=0)
