@@ -21,8 +21,8 @@ VGG_SHIFT = [0, 0, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4]
 
 
 def rel_err(a, b):
-    a, b = a.double(), b.double()
-    return float((a - b).norm() / (b.norm() + 1e-30))
+    a, b = a.detach().double(), b.detach().double()
+    return float((a.detach() - b.detach()).norm() / (b.detach().norm() + 1e-30))
 
 
 def make_sides(h, w, seed=0, channels=VGG_C, shifts=VGG_SHIFT):
@@ -110,7 +110,7 @@ def test_pool_fwd_bwd_vs_dense_mm(layout, dtype, tol):
     maps, _, _ = O.preprocess_superpixels(torch.from_numpy(seg), None)
     g = torch.Generator().manual_seed(1)
     feat_chw = torch.randn(c, h, w, generator=g)
-    ref_in = feat_chw.to(dtype).float().requires_grad_(True)       # oracle sees the same rounded inputs
+    ref_in = feat_chw.to(dtype).float().clone().requires_grad_(True)   # oracle sees the same rounded inputs
     ref = O.pool_dense(maps, ref_in)
     grad = torch.randn(ref.shape, generator=g)
     ref.backward(grad)
@@ -195,7 +195,7 @@ def test_hypercolumn_fwd_bwd_vs_interpolate(layout, h, w):
     ref.backward(grad)
     xs = [s.to(DEV).requires_grad_(True) for s in sides]
     out = ops.hypercolumn(xs, (h, w), layout=layout)
-    got = out.cpu().view(h, w, -1).permute(2, 0, 1) if layout == "hwc" else out.cpu()
+    got = out.detach().cpu().view(h, w, -1).permute(2, 0, 1) if layout == "hwc" else out.detach().cpu()
     assert rel_err(got, ref.detach()) < 1e-6
     np.testing.assert_allclose(got.numpy(), ref.detach().numpy(), rtol=1e-4, atol=1e-5)
     # identity levels are exact copies

@@ -46,7 +46,10 @@ def test_forward_loss_backward_matches_reference(golden, layout):
     pred = model((x, sp_maps))
     assert pred.shape == (1, 48, 40) and pred.dtype == torch.float32
     assert model.feature_maps.shape == (2112, 48, 40)
-    np.testing.assert_allclose(model.feature_maps[:, ::7, ::5].detach().cpu().numpy(), g["feats_probe"], rtol=1e-4, atol=1e-5)
+    probe = model.feature_maps[:, ::7, ::5].detach().cpu()
+    ref_probe = torch.from_numpy(g["feats_probe"])
+    assert float((probe - ref_probe).norm() / ref_probe.norm()) < 1e-5            # 1e-4 relative is the north-star bar
+    np.testing.assert_allclose(probe.numpy(), g["feats_probe"], rtol=1e-4, atol=1e-4)   # cuDNN conv algorithms differ in the last bits
     np.testing.assert_allclose(model.sp_features.detach().cpu().numpy(), g["sp_features"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(model.sp_pred.detach().cpu().numpy(), g["sp_pred"], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(pred.cpu().numpy(), g["pred"], rtol=1e-4, atol=1e-6)
