@@ -144,11 +144,16 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # own arm
 # ---------------------------------------------------------------------------
+QUICK = bool(int(os.environ.get("WESUP_BENCH_QUICK", "0")))     # 1 launch per kernel (ncu --set full captures)
+
+
 def time_kernel(fn, iters, flush):
     """Average device time of `fn` in ms over `iters` launches, CUDA events on the
     current stream, an L2 flush (write of a > L2 buffer) before every launch."""
     import torch
-    for _ in range(3):
+    if QUICK:
+        iters = 1
+    for _ in range(1 if QUICK else 3):
         fn()
     torch.cuda.synchronize()
     total = 0.0
@@ -206,6 +211,14 @@ def kernel_rooflines(dev, peak_gbs):
                          5, flush)
         b = side_bytes + C_HYPER * hw * es
         out[f"hypercolumn_bwd_{tag}"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
+        if dtype == torch.float32:
+            ca, ha, wa = ia(Cs), ia(hs), ia(ws_)
+            fws = torch.empty(lib.wesup_sp_pool_hypercolumn_bwd_workspace_bytes(ca, ha, wa, 13, H, W, n_sp), dtype=torch.uint8, device=dev)
+            ms = time_kernel(lambda: lib.wesup_sp_pool_hypercolumn_bwd(gp.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
+                                                                       ca, ha, wa, 13, H, W, n_sp, ptrs, fws.data_ptr(), st), 10, flush)
+            b = side_bytes + hw * 4 + 2 * n_sp * C_HYPER * 4 + n_sp * 4
+            out["pool_hypercolumn_bwd_fused"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6,
+                                                 "replaces_ms": out["sp_pool_bwd_f32"]["ms"] + out["hypercolumn_bwd_f32"]["ms"]}
         del feats, gf
     ms = time_kernel(lambda: ops.slic(x, int(hw / 200), 40), 10, flush)
     b = hw * 360

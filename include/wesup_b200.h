@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define WESUP_ABI_VERSION 1
+#define WESUP_ABI_VERSION 2
 #define WESUP_MAX_LEVELS 16
 
 /* element type of the hypercolumn tensor */
@@ -96,6 +96,19 @@ int wesup_sp_pool_fwd(const void *feat, int dtype, int layout, const int32_t *se
                       void *stream);
 int wesup_sp_pool_bwd(const float *grad_pooled, const int32_t *row_labels, const int32_t *counts,
                       int HW, int C, int N, void *grad_feat, int dtype, int layout, void *stream);
+
+/* fused adjoint of (b) o (a): what autograd derives for the mm at
+ * models/wesup.py:284-285 followed by the cat + interpolate chain at :254-261,
+ * evaluated from the pooled gradient (N, sum C) directly -- the (H*W, sum C)
+ * gradient of the hypercolumn is never written.  grad_side[l]: fp32
+ * (h[l],w[l],C[l]) pixel-major (WESUP_HWC); C/h/w/grad_side are HOST arrays.
+ * Deterministic (gather form). */
+size_t wesup_sp_pool_hypercolumn_bwd_workspace_bytes(const int *C, const int *h, const int *w,
+                                                     int n_levels, int H, int W, int N);
+int wesup_sp_pool_hypercolumn_bwd(const float *grad_pooled, const int32_t *row_labels,
+                                  const int32_t *counts, const int *C, const int *h, const int *w,
+                                  int n_levels, int H, int W, int N, void *const *grad_side,
+                                  void *ws, void *stream);
 
 /* ---- paint: replaces argmax + per-superpixel index_put loop -----------------
  * (models/wesup.py:295-304): out[p] = sp_pred[row_labels[p], cls]. */

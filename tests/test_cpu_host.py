@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.wesup_abi_version() == 1
+    assert lib.wesup_abi_version() == 2
     out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
     for name in declared:
         assert re.search(rf"\bT {name}\b", out), name
@@ -170,3 +170,43 @@ def test_tiles_match_reference_golden(golden):
         assert np.array_equal(tiles.divide_image_to_patches(img, p), g[f"patches{i}"])
         merged = tiles.combine_patches_to_image(g[f"preds{i}"], h, w)
         assert np.array_equal(merged, g[f"combined{i}"])          # same arithmetic order => bit-exact
+
+
+def test_cli_parses_like_fire():
+    from wesup_b200 import cli
+    args, kw = cli.parse(["data/glas", "--epochs", "3", "--scales=(0.5,1)", "--smoke", "--model", "wesup", "--lr", "5e-5"])
+    assert args == ["data/glas"]
+    assert kw == {"epochs": 3, "scales": (0.5, 1), "smoke": True, "model": "wesup", "lr": 5e-5}
+    assert cli.run(lambda a, b=1, **k: (a, b, k), ["x", "--b", "2", "--c-d", "q"]) == ("x", 2, {"c_d": "q"})
+
+
+def test_disjoint_tile_merge_equals_running_mean():
+    from wesup_b200 import tiles
+    rng = np.random.default_rng(0)
+    for shape in [(12, 5, 5, 2), (12, 5, 5)]:
+        patches = rng.random(shape)
+        assert tiles.tiles_are_disjoint(15, 20, 5) and not tiles.tiles_are_disjoint(16, 20, 5)
+        np.testing.assert_array_equal(tiles.combine_patches_to_image(patches, 15, 20), tiles.combine_disjoint(patches, 15, 20))
+
+
+def test_folder_datasets_follow_the_reference_contract(tmp_path):
+    from PIL import Image
+    from wesup_b200.utils import is_empty_tensor
+    from wesup_b200.utils.data import PointDataset, SegmentationDataset
+    root = tmp_path / "train"
+    for sub in ("images", "masks", "points"):
+        (root / sub).mkdir(parents=True)
+    rng = np.random.default_rng(1)
+    Image.fromarray(rng.integers(0, 255, (20, 30, 3), dtype=np.uint8)).save(root / "images" / "a.png")
+    Image.fromarray(((rng.random((20, 30)) > 0.5) * 255).astype(np.uint8)).save(root / "masks" / "a.png")
+    (root / "points" / "a.csv").write_text("3,4,1\n10,12,0\n")
+    img, mask = SegmentationDataset(root, train=False)[0]
+    assert img.shape == (3, 20, 30) and img.dtype == torch.float32 and 0 <= float(img.min()) and float(img.max()) <= 1
+    assert mask.shape == (2, 20, 30) and mask.dtype == torch.int64 and torch.all(mask.sum(0) == 1)
+    img, pixel_mask, point_mask = PointDataset(root, train=False)[0]
+    assert point_mask.shape == (2, 20, 30) and int(point_mask.sum()) == 2
+    assert int(point_mask[1, 4, 3]) == 1 and int(point_mask[0, 12, 10]) == 1
+    half = SegmentationDataset(root, train=False, rescale_factor=0.5)[0][0]
+    assert half.shape == (3, 10, 15)
+    (root / "masks" / "a.png").unlink(); (root / "masks").rmdir()
+    assert is_empty_tensor(SegmentationDataset(root, train=False)[0][1])

@@ -236,6 +236,53 @@ def test_hypercolumn_adjoint_identity_full_size():
     assert float((const - 2.5).abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("h,w,n", [(48, 40, 30), (37, 51, 7), (16, 16, 256), (131, 97, 60)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_pool_hypercolumn_backward_vs_autograd_of_dense_reference(h, w, n, dtype):
+    """d(side outputs) of `mm(sp_maps, cat(interpolate(side)))` from the fused
+    kernel vs torch autograd of the reference's dense formulation on the CPU, and
+    vs the unfused pool_bwd -> hypercolumn_bwd pair."""
+    gen = torch.Generator().manual_seed(h * w + n)
+    sides = make_sides(h, w, seed=w)
+    seg = torch.randint(0, n, (h, w), generator=gen)
+    seg.view(-1)[:n] = torch.arange(n)                                    # every id present
+    maps, _, _ = O.preprocess_superpixels(seg, None)
+    ref_in = [s.clone().requires_grad_(True) for s in sides]
+    feats = O.hypercolumn_from_sides(ref_in, (h, w))
+    pooled_ref = O.pool_dense(maps, feats)
+    gp = torch.randn(pooled_ref.shape, generator=gen)
+    pooled_ref.backward(gp)
+    sp = SuperpixelMaps.from_labels(seg.to(DEV))
+    xs = [s.to(DEV).requires_grad_(True) for s in sides]
+    pooled, hc = ops.hypercolumn_pool(xs, (h, w), sp, dtype=dtype)
+    assert hc.shape == (h * w, 2112) and hc.dtype == dtype and not hc.requires_grad
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel_err(pooled.cpu(), pooled_ref) < tol
+    pooled.backward(gp.to(DEV))
+    for x, r in zip(xs, ref_in):
+        assert rel_err(x.grad.cpu(), r.grad) < 1e-5                       # backward never touches the bf16 tensor
+    if dtype == torch.float32:
+        ys = [s.to(DEV).requires_grad_(True) for s in sides]
+        ops.sp_pool(ops.hypercolumn(ys, (h, w)), sp).backward(gp.to(DEV))
+        for x, y in zip(xs, ys):
+            assert rel_err(x.grad, y.grad) < 1e-6
+
+
+def test_fused_backward_full_size_adjoint_identity():
+    """<pool(hyper(x)), g> == <x, fused_bwd(g)> at 464^2 with a SLIC-like grid of superpixels."""
+    h = w = 464
+    yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    seg = (yy // 14) * ((w + 13) // 14) + xx // 14
+    sp = SuperpixelMaps.from_labels(seg.to(DEV))
+    xs = [s.to(DEV).requires_grad_(True) for s in make_sides(h, w, seed=2)]
+    pooled, _ = ops.hypercolumn_pool(xs, (h, w), sp)
+    g = torch.randn_like(pooled)
+    pooled.backward(g)
+    lhs = (pooled.detach().double() * g.double()).sum()
+    rhs = sum((x.detach().double() * x.grad.double()).sum() for x in xs)
+    assert abs(float(lhs - rhs)) < 1e-5 * abs(float(lhs)) + 1e-3
+
+
 # ---------------------------------------------------------------------------
 # label propagation (a7)
 # ---------------------------------------------------------------------------

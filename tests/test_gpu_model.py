@@ -33,10 +33,10 @@ def build(cls=WESUP, **kw):
     return model.to(DEV)
 
 
-@pytest.mark.parametrize("layout", ["hwc", "chw"])
-def test_forward_loss_backward_matches_reference(golden, layout):
+@pytest.mark.parametrize("layout,fused", [("hwc", True), ("hwc", False), ("chw", False)])
+def test_forward_loss_backward_matches_reference(golden, layout, fused):
     g = golden("forward_loss_backward_48x40.npz")
-    model = build(hc_layout=layout)
+    model = build(hc_layout=layout, fused_backward=fused)
     trainer = WESUPTrainer(model, device=DEV)
     x = synth.to_tensor(g["img_u8"]).unsqueeze(0).to(DEV)
     sp_maps, sp_labels = _preprocess_superpixels(torch.from_numpy(g["segments"]).to(DEV),

@@ -87,6 +87,30 @@ template <> struct Vec4<__nv_bfloat16> {
     static __device__ __forceinline__ void store(__nv_bfloat16 *p, float4 v) { stg_stream(reinterpret_cast<uint2 *>(p), pack_bf16x4(v)); }
 };
 
+// ---- 16-byte channel groups: V fp32 values in registers, stored as T ---------
+template <int V> struct FVec { float v[V]; };
+
+template <int V> __device__ __forceinline__ FVec<V> ld_group(const float *p) {
+    FVec<V> r;
+#pragma unroll
+    for (int k = 0; k < V / 4; ++k) {
+        float4 t = __ldg(reinterpret_cast<const float4 *>(p) + k);
+        r.v[4 * k] = t.x; r.v[4 * k + 1] = t.y; r.v[4 * k + 2] = t.z; r.v[4 * k + 3] = t.w;
+    }
+    return r;
+}
+__device__ __forceinline__ void st_group(float *p, const FVec<4> &a) {
+    stg_stream(reinterpret_cast<float4 *>(p), make_float4(a.v[0], a.v[1], a.v[2], a.v[3]));
+}
+__device__ __forceinline__ void st_group(__nv_bfloat16 *p, const FVec<8> &a) {
+    uint2 lo = pack_bf16x4(make_float4(a.v[0], a.v[1], a.v[2], a.v[3]));
+    uint2 hi = pack_bf16x4(make_float4(a.v[4], a.v[5], a.v[6], a.v[7]));
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(hi.x), "r"(hi.y) : "memory");
+}
+__device__ __forceinline__ void st_group(__nv_bfloat16 *p, const FVec<4> &a) {
+    stg_stream(reinterpret_cast<uint2 *>(p), pack_bf16x4(make_float4(a.v[0], a.v[1], a.v[2], a.v[3])));
+}
+
 __device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 operator*(float a, float4 b) { return make_float4(a * b.x, a * b.y, a * b.z, a * b.w); }
 __device__ __forceinline__ void fma4(float4 &acc, float w, float4 v) {

@@ -279,6 +279,38 @@ __global__ void __launch_bounds__(256) pool_bwd_hwc_kernel(const float *__restri
     Vec4<T>::store(grad_feat + p * C + c, g);
 }
 
+// Fast path: block = a run of consecutive pixels, thread = one 16-byte channel
+// group.  The (pre-scaled) pooled-gradient row is re-fetched only when the
+// label changes along the walk (superpixels are ~14 px wide), so the kernel is
+// a pure coalesced write stream of C*sizeof(T) bytes per pixel.
+template <typename T, int V>
+__global__ void __launch_bounds__(544) pool_bwd_walk_kernel(const float *__restrict__ grad_pooled, const int32_t *__restrict__ row_labels,
+                                                           const int32_t *__restrict__ counts, int C, int HW, int seg,
+                                                           T *__restrict__ grad_feat) {
+    const int c = threadIdx.x * V;
+    if (c >= C) return;
+    const int p0 = blockIdx.x * seg, p1 = min(p0 + seg, HW);
+    T *o = grad_feat + (long)p0 * C + c;
+    int cur = -2;
+    FVec<V> g;
+    for (int p = p0; p < p1; ++p, o += C) {
+        const int k = __ldg(row_labels + p);
+        if (k != cur) {
+            cur = k;
+            if (k >= 0) {
+                const float inv = 1.0f / (float)__ldg(counts + k);
+                g = ld_group<V>(grad_pooled + (long)k * C + c);
+#pragma unroll
+                for (int j = 0; j < V; ++j) g.v[j] *= inv;
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) g.v[j] = 0.f;
+            }
+        }
+        st_group(o, g);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) pool_bwd_chw_kernel(const float *__restrict__ grad_pooled, const int32_t *__restrict__ row_labels,
                                                           const int32_t *__restrict__ counts, long HW, int C,
@@ -378,7 +410,14 @@ extern "C" int wesup_sp_pool_bwd(const float *grad_pooled, const int32_t *row_la
         long n_items = (long)HW * C4;
         long grid = (n_items + 255) / 256;
         WESUP_REQUIRE(grid < (1L << 31), WESUP_E_UNSUPPORTED, "wesup_sp_pool_bwd: grid too large");
-        if (dtype == WESUP_F32)
+        const int V = dtype == WESUP_F32 ? 4 : 8;
+        if (C % V == 0 && C / V <= 544) {
+            const int seg = 64, threads = (C / V + 31) / 32 * 32;
+            if (dtype == WESUP_F32)
+                pool_bwd_walk_kernel<float, 4><<<cdiv(HW, seg), threads, 0, stream>>>(grad_pooled, row_labels, counts, C, HW, seg, (float *)grad_feat);
+            else
+                pool_bwd_walk_kernel<__nv_bfloat16, 8><<<cdiv(HW, seg), threads, 0, stream>>>(grad_pooled, row_labels, counts, C, HW, seg, (__nv_bfloat16 *)grad_feat);
+        } else if (dtype == WESUP_F32)
             pool_bwd_hwc_kernel<float><<<(unsigned)grid, 256, 0, stream>>>(grad_pooled, row_labels, counts, C, C4, n_items, (float *)grad_feat);
         else
             pool_bwd_hwc_kernel<__nv_bfloat16><<<(unsigned)grid, 256, 0, stream>>>(grad_pooled, row_labels, counts, C, C4, n_items, (__nv_bfloat16 *)grad_feat);

@@ -112,6 +112,8 @@ class WESUP(nn.Module):
       pretrained    load ImageNet VGG16 weights when reachable (default True)
       hc_dtype      torch.float32 (default) or torch.bfloat16 hypercolumn storage
       hc_layout     'hwc' (default, pixel-major) or 'chw' (the reference's layout)
+      fused_backward  True (default): backward of pooling + hypercolumn is one fused
+                    kernel working from the pooled gradient (hwc layout only)
     """
 
     def __init__(self, n_classes=2, D=32, **kwargs):
@@ -134,6 +136,7 @@ class WESUP(nn.Module):
             nn.Linear(D, self.kwargs.get("n_classes", n_classes)), nn.Softmax(dim=1))
         self.hc_dtype = kwargs.get("hc_dtype", torch.float32)
         self.hc_layout = kwargs.get("hc_layout", "hwc")
+        self.fused_backward = bool(kwargs.get("fused_backward", True))
         self.feature_maps = None
         self.fm_size = None
         self.sp_features = None
@@ -168,8 +171,13 @@ class WESUP(nn.Module):
         """x = (image (1,3,H,W), sp_maps); returns class-1 probability (1,H,W)."""
         x, sp_maps = x
         sp = sp_maps if isinstance(sp_maps, SuperpixelMaps) else SuperpixelMaps.from_dense(sp_maps)
-        feats = self._hypercolumn(x)
-        pooled = ops.sp_pool(feats, sp, layout=self.hc_layout)
+        if self.fused_backward and self.hc_layout == "hwc":
+            self.fm_size = (x.size(2), x.size(3))
+            pooled, feats = ops.hypercolumn_pool(self._side_outputs(x), self.fm_size, sp, dtype=self.hc_dtype)
+            self.feature_maps = feats.t().view(-1, *self.fm_size)
+        else:
+            feats = self._hypercolumn(x)
+            pooled = ops.sp_pool(feats, sp, layout=self.hc_layout)
         x = self.fc_layers(pooled)
         self.sp_features = x
         self.sp_pred = self.classifier(x)
@@ -210,12 +218,12 @@ class WESUPTrainer(BaseTrainer):
 
     def get_default_dataset(self, root_dir, train=True, proportion=1.0):
         # PNG/CSV readers and albumentations augmentation are CPU I/O outside this
-        # path; plug the reference's utils.data in.
+        # path: the reference's utils.data is used when
+        # it is on sys.path, else the plain readers of wesup_b200.utils.data.
         try:
-            from utils.data import Digest2019PointDataset, SegmentationDataset  # the reference's, if on sys.path
-        except ImportError as ex:
-            raise RuntimeError("datasets come from the reference's utils/data.py; put it on sys.path "
-                               "(see INTEGRATION.md)") from ex
+            from utils.data import Digest2019PointDataset, SegmentationDataset
+        except ImportError:
+            from ..utils.data import PointDataset as Digest2019PointDataset, SegmentationDataset
         if train:
             if osp.exists(osp.join(root_dir, "points")):
                 return Digest2019PointDataset(root_dir, proportion=proportion,

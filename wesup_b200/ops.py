@@ -241,6 +241,64 @@ def sp_pool(feat: torch.Tensor, sp: SuperpixelMaps, layout: str = "hwc") -> torc
     return _SpPool.apply(feat, sp, _LAYOUTS[layout])
 
 
+class _HypercolumnPool(torch.autograd.Function):
+    """(a) then (b) as one differentiable op over the side outputs.  Forward is the
+    two north-star kernels (the hypercolumn is written once, then pooled);
+    backward is ONE fused kernel that evaluates the adjoint of both from the
+    pooled gradient, so the (H*W, C) gradient is never materialised and nothing
+    of that size is kept for backward (both ops are linear)."""
+
+    @staticmethod
+    def forward(ctx, sp: SuperpixelMaps, size, dtype, *sides):
+        lib = _lib.load()
+        H, W = size
+        for s in sides:
+            _require_cuda(s, "side output")
+            if s.dim() != 4 or s.size(0) != 1 or s.dtype != torch.float32:
+                raise ValueError("side outputs must be fp32 (1,C,h,w)")
+        if sp.height != H or sp.width != W:
+            raise ValueError(f"superpixel map is {sp.height}x{sp.width}, image is {H}x{W}")
+        C = [s.size(1) for s in sides]
+        h = [s.size(2) for s in sides]
+        w = [s.size(3) for s in sides]
+        mem = [_as_hwc(s) for s in sides]
+        ctot = sum(C)
+        dev = sides[0].device
+        feats = torch.empty((H * W, ctot), dtype=dtype, device=dev)
+        check(lib.wesup_hypercolumn_fwd(_lib.ptr_array([m.data_ptr() for m in mem]), _lib.int_array(C), _lib.int_array(h),
+                                        _lib.int_array(w), len(sides), H, W, feats.data_ptr(), _DTYPES[dtype], HWC,
+                                        _stream()), "wesup_hypercolumn_fwd")
+        pooled = torch.empty((sp.n, ctot), dtype=torch.float32, device=dev)
+        check(lib.wesup_sp_pool_fwd(feats.data_ptr(), _DTYPES[dtype], HWC, sp.seg_offsets.data_ptr(),
+                                    sp.seg_pixels.data_ptr(), H * W, ctot, sp.n, pooled.data_ptr(), _stream()),
+              "wesup_sp_pool_fwd")
+        ctx.sp, ctx.geom = sp, (C, h, w, H, W)
+        ctx.mark_non_differentiable(feats)
+        return pooled, feats
+
+    @staticmethod
+    def backward(ctx, grad_pooled, _grad_feats):
+        lib = _lib.load()
+        sp = ctx.sp
+        C, h, w, H, W = ctx.geom
+        grad_pooled = grad_pooled.contiguous().float()
+        dev = grad_pooled.device
+        mem = [torch.empty((1, hh, ww, cc), dtype=torch.float32, device=dev) for cc, hh, ww in zip(C, h, w)]
+        ca, ha, wa = _lib.int_array(C), _lib.int_array(h), _lib.int_array(w)
+        ws = _ws(lib.wesup_sp_pool_hypercolumn_bwd_workspace_bytes(ca, ha, wa, len(C), H, W, sp.n), dev)
+        check(lib.wesup_sp_pool_hypercolumn_bwd(grad_pooled.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
+                                                ca, ha, wa, len(C), H, W, sp.n,
+                                                _lib.ptr_array([m.data_ptr() for m in mem]), ws.data_ptr(), _stream()),
+              "wesup_sp_pool_hypercolumn_bwd")
+        return (None, None, None, *[m.permute(0, 3, 1, 2) for m in mem])
+
+
+def hypercolumn_pool(sides: Sequence[torch.Tensor], size: Tuple[int, int], sp: SuperpixelMaps, dtype=torch.float32):
+    """Hypercolumn (a) + superpixel mean pooling (b) with the fused backward.
+    Returns (pooled (N,C) fp32, feats (H*W,C) `dtype`, non-differentiable)."""
+    return _HypercolumnPool.apply(sp, (int(size[0]), int(size[1])), dtype, *sides)
+
+
 def paint(sp: SuperpixelMaps, sp_pred: torch.Tensor, cls: int = 1) -> torch.Tensor:
     """pred[p] = sp_pred[row(p), cls] -> (1,H,W); replaces the argmax + per-superpixel
     index_put loop (/root/reference/models/wesup.py:295-304)."""

@@ -39,3 +39,58 @@ def combine_patches_to_image(patches: np.ndarray, target_height: int, target_wid
         acc[win] = (acc[win] * seen[win] + tile) / (seen[win] + 1)
         seen[win] += 1.0
     return np.squeeze(acc)
+
+
+# ---------------------------------------------------------------------------
+# tiled inference drivers (superpixel-wise and pixel-wise), sharded over ranks
+# ---------------------------------------------------------------------------
+def tiles_are_disjoint(height: int, width: int, patch_size: int) -> bool:
+    return height % patch_size == 0 and width % patch_size == 0
+
+
+def combine_disjoint(patches: np.ndarray, target_height: int, target_width: int) -> np.ndarray:
+    """Fast path of `combine_patches_to_image` when no two tiles overlap: the
+    running mean of one sample is the sample itself, so tiles are written in
+    place (bit-identical result, no float64 (H,W,C+1) scratch)."""
+    p = patches.shape[1]
+    ny, nx = target_height // p, target_width // p
+    tail = patches.shape[3:]
+    grid = patches.reshape(ny, nx, p, p, *tail)
+    axes = (0, 2, 1, 3) + tuple(range(4, 4 + len(tail)))
+    return np.squeeze(grid.transpose(axes).reshape(target_height, target_width, *tail))
+
+
+def predict_tiles(step, img: np.ndarray, patch_size: int, device, rank: int = 0, world_size: int = 1, group=None,
+                  out_dtype=None):
+    """Run `step(tile_tensor (1,3,p,p) fp32 on device) -> (p,p[,C]) tensor` on the
+    tiles this rank owns (contiguous block of the row-major tile list, so a rank's
+    output is a stripe of the slide), gather the finished tiles to rank 0 in tile
+    order and merge them there.  Returns the merged (H,W[,C]) array on rank 0 and
+    None elsewhere.  Tiles are cut on the host (uint8) and converted to fp32 on
+    the device; nothing but finished predictions travels between ranks
+    (no data-path collective)."""
+    import torch
+    from .parallel import gather_tiles, shard_range
+    height, width = img.shape[:2]
+    coords = top_left_coordinates(height, width, patch_size)
+    lo, hi = shard_range(len(coords), rank, world_size)
+    src = torch.from_numpy(np.ascontiguousarray(img[..., :3]))
+    pinned = src.pin_memory() if torch.cuda.is_available() else src
+    outs = []
+    for t, l in coords[lo:hi]:
+        tile = pinned[t:t + patch_size, l:l + patch_size].to(device, non_blocking=True)
+        x = tile.permute(2, 0, 1).float().div_(255.0).unsqueeze(0).contiguous()       # == TF.to_tensor
+        y = step(x)
+        outs.append(y if out_dtype is None else y.to(out_dtype))
+    if outs:
+        local = torch.stack(outs)
+    else:
+        shape = (patch_size, patch_size)
+        local = torch.zeros((0, *shape), dtype=out_dtype or torch.float32, device=device)
+    stack = gather_tiles(local, len(coords), rank, world_size, group=group)
+    if stack is None:
+        return None
+    patches = stack.cpu().numpy()
+    if tiles_are_disjoint(height, width, patch_size):
+        return combine_disjoint(patches, height, width)
+    return combine_patches_to_image(patches, height, width)
