@@ -225,11 +225,27 @@ def kernel_rooflines(dev, peak_gbs):
     out["slic"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
     ms = time_kernel(lambda: SuperpixelMaps.from_labels(labels, point_mask[0].to(dev), n_sp=n_sp), 10, flush)
     out["sp_stats"] = {"ms": ms, "bytes": hw * 5 + n_sp * 12, "gbs": (hw * 5 + n_sp * 12) / ms / 1e6}
-    f = (torch.randn(n_sp, 32, device=dev) * 0.06).abs()
-    y_l = torch.zeros(sp.n_labeled, 2, device=dev); y_l[:, 0] = 1
-    ms = time_kernel(lambda: ops.label_propagate(f, y_l, 0.8), 10, flush)
-    out["label_propagate"] = {"ms": ms, "flops": 3.0 * (n_sp - sp.n_labeled) * sp.n_labeled * 32,
-                              "n": n_sp, "n_l": sp.n_labeled}
+    # (c) label propagation: realistic (1e-4 point labels) and the microbench stress shape, both paths
+    for tag, n, n_l in (("realistic", n_sp, sp.n_labeled), ("stress", 8000, 4000)):
+        f = (torch.randn(n, 32, device=dev) * 0.06).abs()
+        y_l = torch.zeros(n_l, 2, device=dev); y_l[:, 0] = 1
+        n_u = n - n_l
+        y_u = torch.zeros(n_u, 2, device=dev)
+        src = torch.zeros(n_u, dtype=torch.int32, device=dev)
+        sim = torch.zeros(n_u, device=dev)
+        lws = torch.empty(lib.wesup_label_propagate_workspace_bytes(n, 32, n_l), dtype=torch.uint8, device=dev)
+        for algo in ("exact", "tc"):
+            cfn = getattr(lib, ops._LP_ALGOS[algo])
+            ms = time_kernel(lambda: cfn(f.data_ptr(), n, 32, n_l, y_l.data_ptr(), 2, 0.8, y_u.data_ptr(), src.data_ptr(),
+                                         sim.data_ptr(), lws.data_ptr(), st), 10, flush)
+            entry = {"ms": ms, "n": n, "n_l": n_l, "useful_flops": 2.0 * n_u * n_l * 32,
+                     "useful_tflops": 2.0 * n_u * n_l * 32 / ms / 1e9}
+            if algo == "tc":
+                entry["tensor_flops"] = 2.0 * n_u * n_l * 96           # split-TF32: K' = 3 * 32
+                entry["tensor_tflops"] = entry["tensor_flops"] / ms / 1e9
+                st_ = ops.label_propagate(f, y_l, 0.8, algo="tc", return_stats=True)[-1]
+                entry["exact_reevaluations_per_row"] = st_["exact_evals"] / max(n_u, 1)
+            out[f"label_propagate_{algo}_{tag}"] = entry
     for v in out.values():
         if "gbs" in v:
             v["frac_of_hbm_peak"] = v["gbs"] / peak_gbs
@@ -261,13 +277,20 @@ def run_own(args):
     resident = [tuple(t.to(dev) for t in s) for s in host]
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
-    def step_resident(i):
+    def run_step(samples, i):
+        # the trainer's epoch loop does the same: preprocessing (H2D copy, GPU SLIC, superpixel
+        # statistics) of image k+1 is enqueued on a side stream before image k trains
         for j in range(ips):
-            trainer.train_one_iteration("train", *resident[(i * ips + j) % pool])
+            k = i * ips + j
+            if not args.no_prefetch:
+                trainer.prefetch(*samples[(k + 1) % pool])
+            trainer.train_one_iteration("train", *samples[k % pool])
+
+    def step_resident(i):
+        run_step(resident, i)
 
     def step_host(i):
-        for j in range(ips):
-            trainer.train_one_iteration("train", *host[(i * ips + j) % pool])
+        run_step(host, i)
 
     def barrier():
         if world > 1:
@@ -351,6 +374,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--images-per-step", type=int, default=4)
+    ap.add_argument("--no-prefetch", action="store_true", help="preprocess inline instead of one image ahead on a side stream")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-kernels", action="store_true", help="omit the per-kernel roofline microbench")
     args = ap.parse_args()

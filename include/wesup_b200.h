@@ -121,9 +121,27 @@ int wesup_sp_paint(const int32_t *row_labels, const float *sp_pred, int HW, int 
  * src = first arg-max, y_u[u] = y_l[src] iff sim > thr (strict) else 0.
  * y_u (N-n_l,n_cls); src_idx, max_sim (N-n_l) may be NULL. */
 size_t wesup_label_propagate_workspace_bytes(int N, int D, int n_l);
+/* dispatcher: the tcgen05 path when D == 32 and n_u*n_l is large enough to fill
+ * the tensor pipe (WESUP_LP_TC_MIN_PAIRS, default 16384), else the CUDA-core
+ * path; both give bit-identical src_idx / max_sim / y_u. */
 int wesup_label_propagate(const float *feats, int N, int D, int n_l, const float *y_l, int n_cls,
                           float thr, float *y_u, int32_t *src_idx, float *max_sim, void *ws,
                           void *stream);
+/* CUDA-core path: direct-difference fp32 distances, any D. */
+int wesup_label_propagate_exact(const float *feats, int N, int D, int n_l, const float *y_l,
+                                int n_cls, float thr, float *y_u, int32_t *src_idx, float *max_sim,
+                                void *ws, void *stream);
+/* tensor-core path (D == 32): split-TF32 tcgen05.mma cross term with TMEM
+ * accumulators as a candidate filter + exact fp32 re-evaluation of the
+ * survivors in the epilogue (see csrc/label_propagate_tc.cu). */
+size_t wesup_label_propagate_tc_workspace_bytes(int N, int D, int n_l);
+int wesup_label_propagate_tc(const float *feats, int N, int D, int n_l, const float *y_l, int n_cls,
+                             float thr, float *y_u, int32_t *src_idx, float *max_sim, void *ws,
+                             void *stream);
+/* diagnostics of the last tensor-core call on `ws` (synchronise the stream first;
+ * HOST out[2]): out[0] = exact re-evaluations, out[1] = float bits of
+ * max |approx d2 - exact d2| / (|a|^2 + |b|^2) over the re-evaluated pairs. */
+int wesup_label_propagate_tc_stats(const void *ws, int N, int n_l, unsigned long long *out_host);
 
 /* ---- (d) SLIC: replaces skimage.segmentation.slic at models/wesup.py:471-476
  * rgb: fp32 in [0,1], (3,H,W) for WESUP_CHW (what the trainer holds) or (H,W,3).

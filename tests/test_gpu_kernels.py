@@ -356,6 +356,62 @@ def test_label_propagate_edge_cases():
     assert ops.label_propagate(f2[:3].to(DEV), y_l.to(DEV), 0.5).shape == (0, 2)
 
 
+# ---- tensor-core path (tcgen05): must be bit-identical to the CUDA-core path ----
+TC_KAPPA = 2.0 ** -16
+
+
+def assert_tc_equals_exact(f, y_l, thr):
+    a = ops.label_propagate(f.to(DEV), y_l.to(DEV), thr, return_aux=True, algo="exact")
+    y_u, src, sim, stats = ops.label_propagate(f.to(DEV), y_l.to(DEV), thr, return_aux=True, algo="tc", return_stats=True)
+    assert torch.equal(src, a[1]), f"src differs in {(src != a[1]).sum().item()} rows"
+    assert torch.equal(sim, a[2])                                         # same bits, not just close
+    assert torch.equal(y_u, a[0])
+    assert stats["max_err_ratio"] < 0.5 * TC_KAPPA, stats                 # the filter's error bound holds with margin
+    assert stats["exact_evals"] >= src.numel()
+    return stats
+
+
+@pytest.mark.parametrize("n,n_l,scale", [(300, 1, 0.06), (1076, 21, 0.06), (2022, 40, 0.06), (1500, 750, 0.05),
+                                         (4000, 2000, 0.06), (8000, 4000, 0.06), (513, 129, 0.3), (700, 257, 1.5)])
+def test_label_propagate_tc_is_bit_identical(n, n_l, scale):
+    g = torch.Generator().manual_seed(n + n_l)
+    f = (torch.randn(n, 32, generator=g) * scale).abs()
+    y_l = torch.zeros(n_l, 2)
+    y_l[torch.arange(n_l), torch.randint(0, 2, (n_l,), generator=g)] = 1
+    stats = assert_tc_equals_exact(f, y_l, 0.8)
+    if scale <= 0.06 and n_l >= 40:
+        # separated features: the tensor-core filter leaves only a few exact re-evaluations per row
+        assert stats["exact_evals"] < 0.25 * stats["pairs"], stats
+
+
+def test_label_propagate_tc_collapsed_and_tied_features(golden):
+    """Worst cases for the filter: every labeled row is a candidate (random-init
+    collapse, SURVEY.md section 8d caveat), exact ties, duplicated labeled rows."""
+    y_l = torch.tensor([[1.0, 0.0], [0.0, 1.0], [1.0, 1.0]])
+    same = torch.ones(400, 32) * 0.3
+    y3 = y_l.repeat(50, 1)[:150]
+    y_u, src, sim = ops.label_propagate(same.to(DEV), y3.to(DEV), 0.8, return_aux=True, algo="tc")
+    assert torch.all(src == 0) and torch.all(sim == 1.0)
+    g = torch.Generator().manual_seed(5)
+    base = torch.rand(1, 32, generator=g) * 3.0
+    near = base + torch.randn(1200, 32, generator=g) * 1e-4              # collapsed cloud, large norms
+    yl = torch.zeros(300, 2); yl[:, 0] = 1
+    assert_tc_equals_exact(near.abs(), yl, 0.8)
+    dup = (torch.randn(200, 32, generator=g) * 0.06).abs()
+    dup = torch.cat([dup, dup, dup[:77]])                                 # every unlabeled row has an exact twin (two of them)
+    yl = torch.zeros(200, 2); yl[:, 1] = 1
+    y_u, src, sim = ops.label_propagate(dup.to(DEV), yl.to(DEV), 0.8, return_aux=True, algo="tc")
+    assert src.cpu().tolist() == list(range(200)) + list(range(77)) and torch.all(sim == 1.0)
+    gl = golden("label_propagate_cases.npz")
+    for i in range(4):
+        f, yl = torch.from_numpy(gl[f"f{i}"]), torch.from_numpy(gl[f"yl{i}"])
+        if f.size(1) != 32 or yl.size(0) >= f.size(0):
+            continue
+        for thr in (0.8, 0.95):
+            y_u = ops.label_propagate(f.to(DEV), yl.to(DEV), thr, algo="tc").cpu()
+            np.testing.assert_array_equal(y_u.numpy(), gl[f"yu{i}_{int(thr * 100)}"])
+
+
 # ---------------------------------------------------------------------------
 # SLIC (a1)
 # ---------------------------------------------------------------------------

@@ -177,3 +177,26 @@ def test_preprocess_input_arity():
         initialize_trainer("mild")
     with pytest.raises(RuntimeError):
         trainer.compute_loss(None, (None, l2))       # no forward pass yet
+
+
+def test_prefetched_preprocess_is_identical_and_single_use():
+    trainer = initialize_trainer("wesup", device=DEV, pretrained=False)
+    a = synth.sample(96, 112, index=5, ratio=2e-3)
+    b = synth.sample(96, 112, index=6, ratio=2e-3)
+    (xa, spa), (pma, la) = trainer.preprocess(*a)
+    trainer.prefetch(*a)
+    assert len(trainer._prefetched) == 1
+    (xb, spb), (pmb, lb) = trainer.preprocess(*b)            # different tensors: the staged result must not be used
+    assert spb.n != 0 and len(trainer._prefetched) == 1
+    trainer.prefetch(*b)                                     # a second staged entry does not evict the first
+    (x2, sp2), (pm2, l2) = trainer.preprocess(*a)            # same tensors: picks the staged result up
+    assert len(trainer._prefetched) == 1
+    assert sp2.n == spa.n and sp2.n_labeled == spa.n_labeled
+    for name in ("order", "row_labels", "counts", "seg_offsets", "seg_pixels"):
+        assert torch.equal(getattr(sp2, name), getattr(spa, name)), name
+    assert torch.equal(l2, la) and torch.equal(x2, xa)
+    # a full iteration through the prefetch path
+    trainer.optimizer, _ = trainer.get_default_optimizer()
+    trainer.train_one_iteration("train", *b)
+    assert len(trainer._prefetched) == 0
+    assert np.isfinite(trainer.tracker.history["loss"][-1])

@@ -11,6 +11,8 @@
 //
 // Backward is the exact adjoint in gather form (each low-resolution element
 // sums its footprint in a fixed order): deterministic, no atomics.
+#include <stdlib.h>
+#include <math.h>
 #include "common.cuh"
 
 namespace wesup {
@@ -20,6 +22,8 @@ struct Levels {
     float *dst[WESUP_MAX_LEVELS];         // bwd: side gradients
     int C[WESUP_MAX_LEVELS], h[WESUP_MAX_LEVELS], w[WESUP_MAX_LEVELS], coff[WESUP_MAX_LEVELS];
     float sy[WESUP_MAX_LEVELS], sx[WESUP_MAX_LEVELS];
+    int ncol[WESUP_MAX_LEVELS];           // bulk-staged kernels: staged source columns per row (upper bound per segment)
+    int soff[WESUP_MAX_LEVELS];           // bulk-staged kernels: float offset of the level's staging area
     int n, H, W, Ctot;
 };
 
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(256) hyper_fwd_hwc_kernel(const Levels L, T *_
 // 4-taps-per-output form and the kernel is bound by the HBM write stream.
 // ---------------------------------------------------------------------------
 template <typename T, int V>
-__global__ void __launch_bounds__(544) hyper_fwd_walk_kernel(const Levels L, T *__restrict__ out, int seg) {
+__global__ void __launch_bounds__(V == 4 ? 544 : 288, V == 4 ? 2 : 3) hyper_fwd_walk_kernel(const Levels L, T *__restrict__ out, int seg) {
     const int c = threadIdx.x * V;
     if (c >= L.Ctot) return;
     int l = 0;
@@ -85,25 +89,157 @@ __global__ void __launch_bounds__(544) hyper_fwd_walk_kernel(const Levels L, T *
     const float *__restrict__ src = L.src[l] + (c - L.coff[l]);
     const int y = blockIdx.y;
     const int x0 = blockIdx.x * seg, x1 = min(x0 + seg, L.W);
-    T *o = out + ((long)y * L.W + x0) * L.Ctot + c;
-    if (hl == L.H && wl == L.W) {                     // identity level: exact copy
+    const long ostride = L.Ctot;
+    T *o = out + ((long)y * L.W + x0) * ostride + c;
+    if (hl == L.H && wl == L.W) {                     // identity level: exact copy, 4 loads in flight
         const float *s = src + ((long)y * wl + x0) * Cl;
-        for (int x = x0; x < x1; ++x, s += Cl, o += L.Ctot) st_group(o, ld_group<V>(s));
+        int x = x0;
+        for (; x + 4 <= x1; x += 4, s += 4 * (long)Cl, o += 4 * ostride) {
+            FVec<V> v0 = ld_group<V>(s), v1 = ld_group<V>(s + Cl), v2 = ld_group<V>(s + 2 * (long)Cl), v3 = ld_group<V>(s + 3 * (long)Cl);
+            st_group(o, v0); st_group(o + ostride, v1); st_group(o + 2 * ostride, v2); st_group(o + 3 * ostride, v3);
+        }
+        for (; x < x1; ++x, s += Cl, o += ostride) st_group(o, ld_group<V>(s));
         return;
     }
     const Tap ty = bilinear_tap(y, L.sy[l], hl);
     const float *__restrict__ r0 = src + (long)ty.i0 * wl * Cl;
     const float *__restrict__ r1 = src + (long)ty.i1 * wl * Cl;
     const float sx = L.sx[l];
+    const int last = wl - 1;
+    auto blend = [&](const FVec<V> &a, const FVec<V> &b) {
+        FVec<V> r;
+#pragma unroll
+        for (int k = 0; k < V; ++k) r.v[k] = fmaf(ty.w1, b.v[k], ty.w0 * a.v[k]);
+        return r;
+    };
+    // software pipeline: c0/c1 are the blended columns cur, cur+1; (na, nb) are the raw rows of column
+    // cur+2, requested one advance ahead of their first use so the L2 round trip overlaps the walk
+    int cur = bilinear_tap(x0, sx, wl).i0;
+    FVec<V> c0 = blend(ld_group<V>(r0 + (long)cur * Cl), ld_group<V>(r1 + (long)cur * Cl));
+    int i = min(cur + 1, last);
+    FVec<V> c1 = blend(ld_group<V>(r0 + (long)i * Cl), ld_group<V>(r1 + (long)i * Cl));
+    i = min(cur + 2, last);
+    FVec<V> na = ld_group<V>(r0 + (long)i * Cl), nb = ld_group<V>(r1 + (long)i * Cl);
+    for (int x = x0; x < x1; ++x, o += ostride) {
+        const Tap tx = bilinear_tap(x, sx, wl);
+        if (tx.i0 != cur) {
+            if (tx.i0 == cur + 1) {
+                c0 = c1;
+                c1 = blend(na, nb);
+            } else {                                   // scale > 1 never happens for an upsample; kept for safety
+                c0 = blend(ld_group<V>(r0 + (long)tx.i0 * Cl), ld_group<V>(r1 + (long)tx.i0 * Cl));
+                c1 = blend(ld_group<V>(r0 + (long)tx.i1 * Cl), ld_group<V>(r1 + (long)tx.i1 * Cl));
+            }
+            cur = tx.i0;
+            i = min(cur + 2, last);
+            na = ld_group<V>(r0 + (long)i * Cl);
+            nb = ld_group<V>(r1 + (long)i * Cl);
+        }
+        FVec<V> r;
+#pragma unroll
+        for (int k = 0; k < V; ++k) r.v[k] = fmaf(tx.w1, c1.v[k], tx.w0 * c0.v[k]);
+        st_group(o, r);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// forward, pixel-major, bulk-staged row walk (the default fast path).
+// Same decomposition as hyper_fwd_walk_kernel (block = one output row segment,
+// thread = one 16-byte channel group, whole channel vector stored per step),
+// but the source data never sits on the critical path: one thread per level
+// issues cp.async.bulk (TMA 1-D bulk copies, SASS UBLKCP) of the two source
+// rows x the few source columns the segment touches into shared memory,
+// completion on an mbarrier; the walk then reads columns with conflict-free
+// LDS.128.  With two such CTAs per SM one is always streaming stores while the
+// other waits for its bulk loads, so global-load latency (which balloons while
+// HBM is saturated with writes) no longer throttles the write stream.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <typename T, int V>
+__global__ void __launch_bounds__(V == 4 ? 544 : 288, 2) hyper_fwd_bulk_kernel(const Levels L, T *__restrict__ out, int seg) {
+    extern __shared__ __align__(128) float stage[];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int y = blockIdx.y;
+    const int x0 = blockIdx.x * seg, x1 = min(x0 + seg, L.W);
+    const uint32_t bar = smem_addr(&mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(L.n));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x < L.n) {                            // producer: one thread per level
+        const int l = threadIdx.x;
+        const int Cl = L.C[l], hl = L.h[l], wl = L.w[l];
+        const bool ident = (hl == L.H && wl == L.W);
+        int jlo, jhi, i0, i1;
+        if (ident) { jlo = x0; jhi = x1 - 1; i0 = i1 = y; }
+        else {
+            jlo = bilinear_tap(x0, L.sx[l], wl).i0;
+            jhi = bilinear_tap(x1 - 1, L.sx[l], wl).i1;
+            const Tap ty = bilinear_tap(y, L.sy[l], hl);
+            i0 = ty.i0; i1 = ty.i1;
+        }
+        const uint32_t bytes = (uint32_t)(jhi - jlo + 1) * Cl * 4u;
+        const uint32_t dst0 = smem_addr(stage + L.soff[l]);
+        const uint32_t dst1 = dst0 + (uint32_t)L.ncol[l] * Cl * 4u;
+        const float *g0 = L.src[l] + ((long)i0 * wl + jlo) * Cl;
+        const float *g1 = L.src[l] + ((long)i1 * wl + jlo) * Cl;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(ident ? bytes : 2u * bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst0), "l"(g0), "r"(bytes), "r"(bar) : "memory");
+        if (!ident)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst1), "l"(g1), "r"(bytes), "r"(bar) : "memory");
+    }
+    const int c = threadIdx.x * V;
+    const bool active = c < L.Ctot;
+    int l = 0;
+    while (l + 1 < L.n && c >= L.coff[l + 1]) ++l;
+    const int Cl = L.C[l], hl = L.h[l], wl = L.w[l];
+    const float sx = L.sx[l];
+    const bool ident = (hl == L.H && wl == L.W);
+    const Tap ty = bilinear_tap(y, L.sy[l], hl);
+    const int jlo = ident ? x0 : bilinear_tap(x0, sx, wl).i0;
+    const float *s0 = stage + L.soff[l] + (c - L.coff[l]) - (long)jlo * Cl;   // column j lives at s0 + j*Cl
+    const float *s1 = s0 + (long)L.ncol[l] * Cl;
+    T *o = out + ((long)y * L.W + x0) * L.Ctot + c;
+    const long ostride = L.Ctot;
+    {                                                   // wait for the bulk copies (phase 0)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "HC_WAIT:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+            "@p bra HC_DONE;\n\t"
+            "bra HC_WAIT;\n\t"
+            "HC_DONE:\n\t"
+            "}\n" ::"r"(bar) : "memory");
+    }
+    if (!active) return;
+    auto lds = [](const float *p) {
+        FVec<V> r;
+#pragma unroll
+        for (int k = 0; k < V / 4; ++k) {
+            float4 t = *reinterpret_cast<const float4 *>(p + 4 * k);
+            r.v[4 * k] = t.x; r.v[4 * k + 1] = t.y; r.v[4 * k + 2] = t.z; r.v[4 * k + 3] = t.w;
+        }
+        return r;
+    };
+    if (ident) {
+#pragma unroll 4
+        for (int x = x0; x < x1; ++x, o += ostride) st_group(o, lds(s0 + (long)x * Cl));
+        return;
+    }
     auto column = [&](int i) {
-        FVec<V> a = ld_group<V>(r0 + (long)i * Cl), b = ld_group<V>(r1 + (long)i * Cl), r;
+        FVec<V> a = lds(s0 + (long)i * Cl), b = lds(s1 + (long)i * Cl), r;
 #pragma unroll
         for (int k = 0; k < V; ++k) r.v[k] = fmaf(ty.w1, b.v[k], ty.w0 * a.v[k]);
         return r;
     };
     int cur = -2;
     FVec<V> c0, c1;
-    for (int x = x0; x < x1; ++x, o += L.Ctot) {
+    for (int x = x0; x < x1; ++x, o += ostride) {
         const Tap tx = bilinear_tap(x, sx, wl);
         if (tx.i0 != cur) {
             c0 = (tx.i0 == cur + 1) ? c1 : column(tx.i0);
@@ -115,6 +251,160 @@ __global__ void __launch_bounds__(544) hyper_fwd_walk_kernel(const Levels L, T *
         for (int k = 0; k < V; ++k) r.v[k] = fmaf(tx.w1, c1.v[k], tx.w0 * c0.v[k]);
         st_group(o, r);
     }
+}
+
+// ---------------------------------------------------------------------------
+// forward, pixel-major, PERSISTENT double-buffered variant of the bulk-staged
+// walk: one CTA per SM loops over (row, segment) tiles; while the CTA streams
+// the stores of tile t from stage t&1, the bulk copies of tile t+1 land in the
+// other stage (one mbarrier per stage, phase = use count parity).  Loads are
+// completely off the critical path: the kernel is a pure HBM write stream.
+// ---------------------------------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(V == 4 ? 544 : 288, 1) hyper_fwd_pipe_kernel(const Levels L, T *__restrict__ out, int seg, int nseg,
+                                                                              int n_tiles, int stage_floats) {
+    extern __shared__ __align__(128) float stage[];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    const uint32_t bar0 = smem_addr(&mbar[0]);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0), "r"(L.n));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u), "r"(L.n));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // per-thread level constants
+    const int c = threadIdx.x * V;
+    const bool active = c < L.Ctot;
+    int l = 0;
+    while (l + 1 < L.n && c >= L.coff[l + 1]) ++l;
+    const int Cl = L.C[l], hl = L.h[l], wl = L.w[l];
+    const float sx = L.sx[l], sy = L.sy[l];
+    const bool ident = (hl == L.H && wl == L.W);
+    const int lane_off = L.soff[l] + (c - L.coff[l]);
+    const long row_floats = (long)L.ncol[l] * Cl;
+    const long ostride = L.Ctot;
+    // producer constants (threads 0 .. n-1 each own one level)
+    const bool producer = threadIdx.x < L.n;
+    const int pl = producer ? threadIdx.x : 0;
+    const int pC = L.C[pl], ph = L.h[pl], pw = L.w[pl];
+    const bool pident = (ph == L.H && pw == L.W);
+
+    auto issue = [&](int tile, int st) {               // called by producer threads only
+        const int y = tile / nseg, x0 = (tile - y * nseg) * seg, x1 = min(x0 + seg, L.W);
+        int jlo, jhi, i0, i1;
+        if (pident) { jlo = x0; jhi = x1 - 1; i0 = i1 = y; }
+        else {
+            jlo = bilinear_tap(x0, L.sx[pl], pw).i0;
+            jhi = bilinear_tap(x1 - 1, L.sx[pl], pw).i1;
+            const Tap ty = bilinear_tap(y, L.sy[pl], ph);
+            i0 = ty.i0; i1 = ty.i1;
+        }
+        const uint32_t bytes = (uint32_t)(jhi - jlo + 1) * pC * 4u;
+        const uint32_t bar = bar0 + 8u * st;
+        const uint32_t dst0 = smem_addr(stage + (long)st * stage_floats + L.soff[pl]);
+        const uint32_t dst1 = dst0 + (uint32_t)L.ncol[pl] * pC * 4u;
+        const float *g0 = L.src[pl] + ((long)i0 * pw + jlo) * pC;
+        const float *g1 = L.src[pl] + ((long)i1 * pw + jlo) * pC;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(pident ? bytes : 2u * bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst0), "l"(g0), "r"(bytes), "r"(bar) : "memory");
+        if (!pident)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst1), "l"(g1), "r"(bytes), "r"(bar) : "memory");
+    };
+    auto lds = [](const float *p) {
+        FVec<V> r;
+#pragma unroll
+        for (int k = 0; k < V / 4; ++k) {
+            float4 t = *reinterpret_cast<const float4 *>(p + 4 * k);
+            r.v[4 * k] = t.x; r.v[4 * k + 1] = t.y; r.v[4 * k + 2] = t.z; r.v[4 * k + 3] = t.w;
+        }
+        return r;
+    };
+
+    __syncthreads();                                    // barrier init visible
+    int tile = blockIdx.x;
+    if (producer && tile < n_tiles) issue(tile, 0);
+    for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
+        const int st = it & 1;
+        __syncthreads();                                // every warp finished tile it-1 => stage st^1 is free
+        if (producer && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x, st ^ 1);
+        {                                               // wait for this tile's bulk copies
+            const uint32_t bar = bar0 + 8u * st, parity = (uint32_t)(it >> 1) & 1u;
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "HCP_WAIT:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@p bra HCP_DONE;\n\t"
+                "bra HCP_WAIT;\n\t"
+                "HCP_DONE:\n\t"
+                "}\n" ::"r"(bar), "r"(parity) : "memory");
+        }
+        if (!active) continue;
+        const int y = tile / nseg, x0 = (tile - y * nseg) * seg, x1 = min(x0 + seg, L.W);
+        T *o = out + ((long)y * L.W + x0) * ostride + c;
+        const float *base = stage + (long)st * stage_floats + lane_off;
+        if (ident) {
+            const float *s0 = base - (long)x0 * Cl;
+#pragma unroll 4
+            for (int x = x0; x < x1; ++x, o += ostride) st_group(o, lds(s0 + (long)x * Cl));
+            continue;
+        }
+        const Tap ty = bilinear_tap(y, sy, hl);
+        const int jlo = bilinear_tap(x0, sx, wl).i0;
+        const float *s0 = base - (long)jlo * Cl;        // column j lives at s0 + j*Cl
+        const float *s1 = s0 + row_floats;
+        auto column = [&](int i) {
+            FVec<V> a = lds(s0 + (long)i * Cl), b = lds(s1 + (long)i * Cl), r;
+#pragma unroll
+            for (int k = 0; k < V; ++k) r.v[k] = fmaf(ty.w1, b.v[k], ty.w0 * a.v[k]);
+            return r;
+        };
+        int cur = -2;
+        FVec<V> c0, c1;
+        for (int x = x0; x < x1; ++x, o += ostride) {
+            const Tap tx = bilinear_tap(x, sx, wl);
+            if (tx.i0 != cur) {
+                c0 = (tx.i0 == cur + 1) ? c1 : column(tx.i0);
+                c1 = (tx.i1 != tx.i0) ? column(tx.i1) : c0;
+                cur = tx.i0;
+            }
+            FVec<V> r;
+#pragma unroll
+            for (int k = 0; k < V; ++k) r.v[k] = fmaf(tx.w1, c1.v[k], tx.w0 * c0.v[k]);
+            st_group(o, r);
+        }
+    }
+}
+
+template <typename T, int V>
+static cudaError_t launch_pipe(const Levels &L, size_t stage_bytes, T *out, int seg, int H, int W, cudaStream_t stream) {
+    static size_t configured = 0;
+    const size_t smem = 2 * stage_bytes;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(hyper_fwd_pipe_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int threads = (L.Ctot / V + 31) / 32 * 32;
+    const int nseg = cdiv(W, seg);
+    const long n_tiles = (long)nseg * H;
+    const int grid = (int)(n_tiles < kNumSMs ? n_tiles : kNumSMs);
+    hyper_fwd_pipe_kernel<T, V><<<grid, threads, smem, stream>>>(L, out, seg, nseg, (int)n_tiles, (int)(stage_bytes / 4));
+    return cudaSuccess;
+}
+
+template <typename T, int V>
+static cudaError_t launch_bulk(const Levels &L, size_t smem, T *out, int seg, int H, int W, cudaStream_t stream) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(hyper_fwd_bulk_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int threads = (L.Ctot / V + 31) / 32 * 32;
+    hyper_fwd_bulk_kernel<T, V><<<dim3(cdiv(W, seg), H), threads, smem, stream>>>(L, out, seg);
+    return cudaSuccess;
 }
 
 // forward, channel-major: one thread per (channel, y, 4 consecutive x)
@@ -273,10 +563,46 @@ extern "C" int wesup_hypercolumn_fwd(const void *const *side, const int *C, cons
         WESUP_REQUIRE(aligned16(out), WESUP_E_ALIGN, "wesup_hypercolumn_fwd: out not 16-byte aligned");
         // fast path: one thread per 16-byte channel group, whole channel vector per block
         const int V = out_dtype == WESUP_F32 ? 4 : 8;
-        bool walk = (L.Ctot % V == 0) && (L.Ctot / V <= 544) && H <= 65535;
+        bool walk = (L.Ctot % V == 0) && (L.Ctot / V <= (V == 4 ? 544 : 288)) && H <= 65535;
         for (int l = 0; l < n_levels; ++l) walk = walk && (C[l] % V == 0);
-        if (walk) {
-            const int seg = 64;
+        // 1 (default): bulk-staged walk, two CTAs per SM; 2: persistent double-buffered; 0: plain walk
+        static const int variant = getenv("WESUP_HC_FWD") ? atoi(getenv("WESUP_HC_FWD")) : 1;
+        static const int seg_env = getenv("WESUP_HC_SEG") ? atoi(getenv("WESUP_HC_SEG")) : 0;
+        static const int bf16_v = getenv("WESUP_HC_BF16_V") ? atoi(getenv("WESUP_HC_BF16_V")) : 8;
+        const size_t smem_cap = (variant == 2 ? 110 : 110) * 1024;      // two stages / two CTAs per SM
+        auto plan = [&](int sg) {
+            size_t bytes = 0;
+            for (int l = 0; l < n_levels; ++l) {
+                const bool ident = (h[l] == H && w[l] == W);
+                int ncol = ident ? sg : (int)floorf((float)(sg - 1) * L.sx[l]) + 3;
+                if (ncol > w[l]) ncol = w[l];
+                L.ncol[l] = ncol;
+                L.soff[l] = (int)(bytes / 4);
+                bytes += (size_t)(ident ? 1 : 2) * ncol * C[l] * 4;
+            }
+            return bytes;
+        };
+        size_t smem = 0;
+        int bseg = seg_env;
+        if (walk && variant >= 1) {
+            if (bseg > 0) smem = plan(bseg);
+            else                                                       // longest segment whose staging fits
+                for (bseg = 32; bseg >= 8; bseg -= 4)
+                    if ((smem = plan(bseg)) <= smem_cap) break;
+            if (bseg < 8) smem = smem_cap + 1;
+        }
+        const bool staged_ok = walk && variant >= 1 && smem <= smem_cap && n_levels <= 32;
+        if (staged_ok && variant == 2 && (long)cdiv(W, bseg) * H < (1L << 31)) {
+            cudaError_t e = out_dtype == WESUP_F32 ? launch_pipe<float, 4>(L, smem, (float *)out, bseg, H, W, stream)
+                                                   : launch_pipe<__nv_bfloat16, 8>(L, smem, (__nv_bfloat16 *)out, bseg, H, W, stream);
+            WESUP_REQUIRE(e == cudaSuccess, (int)e, "wesup_hypercolumn_fwd: %s", cudaGetErrorString(e));
+        } else if (staged_ok) {
+            cudaError_t e = out_dtype == WESUP_F32 ? launch_bulk<float, 4>(L, smem, (float *)out, bseg, H, W, stream)
+                            : bf16_v == 4          ? launch_bulk<__nv_bfloat16, 4>(L, smem, (__nv_bfloat16 *)out, bseg, H, W, stream)
+                                                   : launch_bulk<__nv_bfloat16, 8>(L, smem, (__nv_bfloat16 *)out, bseg, H, W, stream);
+            WESUP_REQUIRE(e == cudaSuccess, (int)e, "wesup_hypercolumn_fwd: %s", cudaGetErrorString(e));
+        } else if (walk) {
+            const int seg = seg_env > 0 ? seg_env : 64;
             const int threads = (L.Ctot / V + 31) / 32 * 32;
             dim3 grid(cdiv(W, seg), H);
             if (out_dtype == WESUP_F32) hyper_fwd_walk_kernel<float, 4><<<grid, threads, 0, stream>>>(L, (float *)out, seg);

@@ -8,6 +8,7 @@
 // Exact path (this file): direct-difference fp32, d2 = sum_k (f_uk - f_jk)^2,
 // sim = expf(-d2), first arg-max on sim (ties -> lowest labeled index, exactly
 // like torch.max on the reference's W_ul), strict `sim > thr`.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace wesup {
@@ -92,13 +93,40 @@ __global__ void __launch_bounds__(LP_THREADS) label_propagate_generic_kernel(
 
 using namespace wesup;
 
-extern "C" size_t wesup_label_propagate_workspace_bytes(int N, int D, int n_l) {
-    (void)N; (void)D; (void)n_l;
-    return 256;   // the exact path needs none; kept non-zero so callers always pass a valid pointer
+extern "C" size_t wesup_label_propagate_tc_workspace_bytes(int N, int D, int n_l);
+extern "C" int wesup_label_propagate_tc(const float *feats, int N, int D, int n_l, const float *y_l, int n_cls, float thr,
+                                        float *y_u, int32_t *src_idx, float *max_sim, void *ws, void *stream_);
+
+// Pairs (n_u * n_l) from which the tensor-core path is taken; below it the whole
+// problem is a handful of CTAs and the single-launch CUDA-core kernel wins on latency.
+static long tc_min_pairs() {
+    static long v = -1;
+    if (v < 0) {
+        const char *e = getenv("WESUP_LP_TC_MIN_PAIRS");
+        v = e ? atol(e) : 16384;
+        if (v < 0) v = 0;
+    }
+    return v;
 }
+
+extern "C" size_t wesup_label_propagate_workspace_bytes(int N, int D, int n_l) {
+    size_t tc = D == 32 ? wesup_label_propagate_tc_workspace_bytes(N, D, n_l) : 0;
+    return tc > 256 ? tc : 256;   // the exact path needs none; non-zero so callers always pass a valid pointer
+}
+
+extern "C" int wesup_label_propagate_exact(const float *feats, int N, int D, int n_l, const float *y_l, int n_cls, float thr,
+                                           float *y_u, int32_t *src_idx, float *max_sim, void *ws, void *stream_);
 
 extern "C" int wesup_label_propagate(const float *feats, int N, int D, int n_l, const float *y_l, int n_cls, float thr,
                                      float *y_u, int32_t *src_idx, float *max_sim, void *ws, void *stream_) {
+    if (feats && ws && D == 32 && n_l > 0 && n_l < N && aligned16(feats) && aligned16(ws) &&
+        (long)(N - n_l) * n_l >= tc_min_pairs())
+        return wesup_label_propagate_tc(feats, N, D, n_l, y_l, n_cls, thr, y_u, src_idx, max_sim, ws, stream_);
+    return wesup_label_propagate_exact(feats, N, D, n_l, y_l, n_cls, thr, y_u, src_idx, max_sim, ws, stream_);
+}
+
+extern "C" int wesup_label_propagate_exact(const float *feats, int N, int D, int n_l, const float *y_l, int n_cls, float thr,
+                                           float *y_u, int32_t *src_idx, float *max_sim, void *ws, void *stream_) {
     (void)ws;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WESUP_REQUIRE(feats && y_l && y_u, WESUP_E_ARG, "wesup_label_propagate: null pointer");

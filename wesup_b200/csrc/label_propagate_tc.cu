@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(TC_THREADS) label_propagate_tc_kernel(
 
     for (int j0 = j_begin; j0 < j_end; j0 += TC_N) {
         const int rows = min(TC_N, j_end - j0);
+        if (j0 != j_begin) __syncthreads();        // every warp is done reading the previous tile's bf / nb
         // ---- stage the labeled tile: split operand, fp32 copy, norms ----------
         {
             float4 row[TC_D / 4];

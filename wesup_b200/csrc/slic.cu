@@ -18,11 +18,20 @@ namespace wesup {
 
 typedef unsigned long long u64;
 
+constexpr int BIN_CAP = 8;          // centres per bin before spilling to the overflow list
+
 struct SlicWs {
     double *lab;        // 3 planes, H*W each (already scaled by 1/compactness)
     double *cent;       // K*5: y,x,L,a,b
+    // ---- region zeroed by one memset at the start of every call ----
     u64 *acc_n;         // K*3: count, sum y, sum x  (exact integer sums)
     double *acc_c;      // K*3: sum L,a,b
+    int32_t *bin_count; // cells: centres binned by floor(c / step)
+    int32_t *ov_count;  // 1: length of the overflow list
+    uint32_t *ticket;   // 1: blocks that finished the current sweep
+    // -----------------------------------------------------------------
+    int32_t *bin_items; // cells*BIN_CAP
+    int32_t *ov_items;  // K
     int32_t *nearest;   // H*W raw k-means assignment
     int32_t *parent;    // H*W union-find / component root (min pixel id)
     int32_t *size;      // H*W component size at its root
@@ -32,26 +41,42 @@ struct SlicWs {
     int32_t *adj_root;  // H*W (at roots) root of the adjacent component or -1
     int32_t *block_sums;// scan scratch
     uint8_t *seen;      // H*W
+    size_t zero_bytes;  // length of the zeroed region (starts at acc_n)
+    int cells_y, cells_x;
 };
 
 static inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 constexpr int SCAN_ELEMS = 4096;    // per block (1024 threads x 4)
 
-static size_t slic_ws_bytes(long HW, long K) {
-    long nblk = (HW + SCAN_ELEMS - 1) / SCAN_ELEMS + 1;
-    return up256(sizeof(double) * 3 * HW) + up256(sizeof(double) * 5 * K) + up256(sizeof(u64) * 3 * K) +
-           up256(sizeof(double) * 3 * K) + 7 * up256(sizeof(int32_t) * HW) + up256(sizeof(int32_t) * 2 * nblk) +
-           up256(HW);
+static inline long n_cells(int H, int W, int step, int *cy, int *cx) {
+    *cy = (H + step - 1) / step;
+    *cx = (W + step - 1) / step;
+    return (long)(*cy) * (*cx);
 }
 
-static SlicWs carve_slic(void *ws, long HW, long K) {
+static size_t slic_ws_bytes(long HW, long K, long cells) {
+    long nblk = (HW + SCAN_ELEMS - 1) / SCAN_ELEMS + 1;
+    return up256(sizeof(double) * 3 * HW) + up256(sizeof(double) * 5 * K) + up256(sizeof(u64) * 3 * K) +
+           up256(sizeof(double) * 3 * K) + up256(sizeof(int32_t) * cells) + 256 + 256 +
+           up256(sizeof(int32_t) * cells * BIN_CAP) + up256(sizeof(int32_t) * K) +
+           7 * up256(sizeof(int32_t) * HW) + up256(sizeof(int32_t) * 2 * nblk) + up256(HW);
+}
+
+static SlicWs carve_slic(void *ws, long HW, long K, long cells) {
     char *p = static_cast<char *>(ws);
     SlicWs s;
     long nblk = (HW + SCAN_ELEMS - 1) / SCAN_ELEMS + 1;
     s.lab = (double *)p;        p += up256(sizeof(double) * 3 * HW);
     s.cent = (double *)p;       p += up256(sizeof(double) * 5 * K);
+    char *z0 = p;
     s.acc_n = (u64 *)p;         p += up256(sizeof(u64) * 3 * K);
     s.acc_c = (double *)p;      p += up256(sizeof(double) * 3 * K);
+    s.bin_count = (int32_t *)p; p += up256(sizeof(int32_t) * cells);
+    s.ov_count = (int32_t *)p;  p += 256;
+    s.ticket = (uint32_t *)p;   p += 256;
+    s.zero_bytes = (size_t)(p - z0);
+    s.bin_items = (int32_t *)p; p += up256(sizeof(int32_t) * cells * BIN_CAP);
+    s.ov_items = (int32_t *)p;  p += up256(sizeof(int32_t) * K);
     s.nearest = (int32_t *)p;   p += up256(sizeof(int32_t) * HW);
     s.parent = (int32_t *)p;    p += up256(sizeof(int32_t) * HW);
     s.size = (int32_t *)p;      p += up256(sizeof(int32_t) * HW);
@@ -108,106 +133,201 @@ __global__ void slic_lab_kernel(const float *__restrict__ rgb, int layout, long 
     lab[2 * HW + p] = __dmul_rn(__dmul_rn(200.0, __dadd_rn(f[1], -f[2])), ratio);
 }
 
+// Bin a centre by the cell that contains it (cell edge = step pixels); NaN centres
+// (empty clusters) are not binned and therefore never become candidates.
+__device__ __forceinline__ void bin_insert(const SlicWs &s, int k, double cy, double cx, int step) {
+    if (!(cy == cy) || !(cx == cx)) return;
+    int by = (int)(cy / (double)step), bx = (int)(cx / (double)step);
+    by = min(max(by, 0), s.cells_y - 1);
+    bx = min(max(bx, 0), s.cells_x - 1);
+    const int cell = by * s.cells_x + bx;
+    const int slot = atomicAdd(&s.bin_count[cell], 1);
+    if (slot < BIN_CAP) s.bin_items[cell * BIN_CAP + slot] = k;
+    else s.ov_items[atomicAdd(s.ov_count, 1)] = k;
+}
+
+// seeds (and their bins) + the per-pixel state of the connectivity pass; the
+// accumulators / bin counters were zeroed by the memset that precedes this launch
 __global__ void slic_init_kernel(SlicWs s, long K, int nx, int step, int start, long HW) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < K) {
-        s.cent[5 * i + 0] = (double)(start + (int)(i / nx) * step);
-        s.cent[5 * i + 1] = (double)(start + (int)(i % nx) * step);
+        const double cy = (double)(start + (int)(i / nx) * step), cx = (double)(start + (int)(i % nx) * step);
+        s.cent[5 * i + 0] = cy;
+        s.cent[5 * i + 1] = cx;
         s.cent[5 * i + 2] = 0.0; s.cent[5 * i + 3] = 0.0; s.cent[5 * i + 4] = 0.0;
-        s.acc_n[3 * i] = 0; s.acc_n[3 * i + 1] = 0; s.acc_n[3 * i + 2] = 0;
-        s.acc_c[3 * i] = 0.0; s.acc_c[3 * i + 1] = 0.0; s.acc_c[3 * i + 2] = 0.0;
+        bin_insert(s, (int)i, cy, cx, step);
     }
-    if (i < HW) s.nearest[i] = 0;
+    if (i < HW) { s.nearest[i] = 0; s.parent[i] = (int)i; s.size[i] = 0; s.seen[i] = 0; s.adj_root[i] = -1; }
 }
 
 // ---------------------------------------------------------------------------
-// assignment + accumulation of the new cluster sums
+// One k-means sweep = ONE launch: assignment, accumulation of the new cluster
+// sums (pre-aggregated per tile in shared memory), and -- in the block that
+// finishes last -- the centre update and the re-binning for the next sweep.
 // ---------------------------------------------------------------------------
 constexpr int AT = 16;              // tile edge
-constexpr int ACHUNK = 256;         // centres examined per round (= block size)
+constexpr int MAX_CAND = 192;       // candidate centres kept in shared memory per tile
 
 struct Cand {
     double cy, cx, l, a, b;
     int k, y0, y1, x0, x1;
 };
 
-__global__ void __launch_bounds__(256) slic_assign_kernel(SlicWs s, int H, int W, long K, int step, double spatial_weight) {
-    __shared__ Cand cand[ACHUNK];
-    __shared__ int n_cand;
+__global__ void __launch_bounds__(256) slic_sweep_kernel(SlicWs s, int H, int W, long K, int step, double spatial_weight) {
+    __shared__ Cand cand[MAX_CAND];
+    __shared__ double acc_c[MAX_CAND][3];
+    __shared__ unsigned int acc_n[MAX_CAND][3];
+    __shared__ int n_cand_s, is_last;
+    const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * AT, ty0 = blockIdx.y * AT;
-    const int x = tx0 + (threadIdx.x & (AT - 1)), y = ty0 + (threadIdx.x >> 4);
+    const int x = tx0 + (tid & (AT - 1)), y = ty0 + (tid >> 4);
     const bool live = x < W && y < H;
     const long HW = (long)H * W;
     const long p = (long)y * W + x;
     double pl = 0, pa = 0, pb = 0;
     if (live) { pl = s.lab[p]; pa = s.lab[HW + p]; pb = s.lab[2 * HW + p]; }
-    double best = CUDART_INF;
-    int best_k = -1;
+    if (tid == 0) n_cand_s = 0;
+    for (int i = tid; i < MAX_CAND; i += 256) {
+        acc_c[i][0] = 0.0; acc_c[i][1] = 0.0; acc_c[i][2] = 0.0;
+        acc_n[i][0] = 0u; acc_n[i][1] = 0u; acc_n[i][2] = 0u;
+    }
+    __syncthreads();
+    // ---- gather the centres whose 2S window intersects this tile -------------
     const double two_s = (double)(2 * step);
-    for (long base = 0; base < K; base += ACHUNK) {
-        __syncthreads();
-        if (threadIdx.x == 0) n_cand = 0;
-        __syncthreads();
-        long k = base + threadIdx.x;
-        if (k < K) {
-            double cy = s.cent[5 * k], cx = s.cent[5 * k + 1];
-            if (cy == cy && cx == cx) {          // NaN centres (empty clusters) never win
-                double lo;
-                lo = cy - two_s;       int y0 = (int)(lo > 0.0 ? lo : 0.0);
-                lo = cy + two_s + 1.0; int y1 = (int)(lo < (double)H ? lo : (double)H);
-                lo = cx - two_s;       int x0 = (int)(lo > 0.0 ? lo : 0.0);
-                lo = cx + two_s + 1.0; int x1 = (int)(lo < (double)W ? lo : (double)W);
-                if (y0 < ty0 + AT && y1 > ty0 && x0 < tx0 + AT && x1 > tx0) {
-                    int slot = atomicAdd(&n_cand, 1);
-                    Cand c;
-                    c.cy = cy; c.cx = cx; c.l = s.cent[5 * k + 2]; c.a = s.cent[5 * k + 3]; c.b = s.cent[5 * k + 4];
-                    c.k = (int)k; c.y0 = y0; c.y1 = y1; c.x0 = x0; c.x1 = x1;
-                    cand[slot] = c;
-                }
+    auto consider = [&](int k) {
+        const double cy = s.cent[5 * k], cx = s.cent[5 * k + 1];
+        double lo;
+        lo = cy - two_s;       const int y0 = (int)(lo > 0.0 ? lo : 0.0);
+        lo = cy + two_s + 1.0; const int y1 = (int)(lo < (double)H ? lo : (double)H);
+        lo = cx - two_s;       const int x0 = (int)(lo > 0.0 ? lo : 0.0);
+        lo = cx + two_s + 1.0; const int x1 = (int)(lo < (double)W ? lo : (double)W);
+        if (y0 < ty0 + AT && y1 > ty0 && x0 < tx0 + AT && x1 > tx0) {
+            const int slot = atomicAdd(&n_cand_s, 1);
+            if (slot < MAX_CAND) {
+                Cand c;
+                c.cy = cy; c.cx = cx; c.l = s.cent[5 * k + 2]; c.a = s.cent[5 * k + 3]; c.b = s.cent[5 * k + 4];
+                c.k = k; c.y0 = y0; c.y1 = y1; c.x0 = x0; c.x1 = x1;
+                cand[slot] = c;
             }
         }
-        __syncthreads();
+    };
+    {
+        // a centre can reach the tile only from cells within 2S+1 pixels of it
+        const int reach = 2 * step + 1;
+        const int by0 = max((ty0 - reach) / step - 1, 0), by1 = min((ty0 + AT - 1 + reach) / step, s.cells_y - 1);
+        const int bx0 = max((tx0 - reach) / step - 1, 0), bx1 = min((tx0 + AT - 1 + reach) / step, s.cells_x - 1);
+        const int nbx = bx1 - bx0 + 1, ncell = (by1 - by0 + 1) * nbx;
+        for (int i = tid; i < ncell * BIN_CAP; i += 256) {
+            const int cell = (by0 + (i / BIN_CAP) / nbx) * s.cells_x + bx0 + (i / BIN_CAP) % nbx;
+            const int slot = i % BIN_CAP;
+            if (slot < min(s.bin_count[cell], BIN_CAP)) consider(s.bin_items[cell * BIN_CAP + slot]);
+        }
+        const int n_ov = *s.ov_count;
+        for (int i = tid; i < n_ov; i += 256) consider(s.ov_items[i]);
+    }
+    __syncthreads();
+    const int n_total = n_cand_s;
+    const int n = min(n_total, MAX_CAND);
+    double best = CUDART_INF;
+    int best_k = -1, best_slot = -1;
+    if (live) {
+        for (int i = 0; i < n; ++i) {
+            const Cand &c = cand[i];
+            if (y < c.y0 || y >= c.y1 || x < c.x0 || x >= c.x1) continue;
+            double dy = __dadd_rn(c.cy, -(double)y); dy = __dmul_rn(dy, dy);
+            double dx = __dadd_rn(c.cx, -(double)x); dx = __dmul_rn(dx, dx);
+            double d = __dmul_rn(__dadd_rn(dy, dx), spatial_weight);
+            double t = __dadd_rn(pl, -c.l);
+            double dc = __dmul_rn(t, t);                       // 0 + t*t
+            t = __dadd_rn(pa, -c.a); dc = __dadd_rn(dc, __dmul_rn(t, t));
+            t = __dadd_rn(pb, -c.b); dc = __dadd_rn(dc, __dmul_rn(t, t));
+            d = __dadd_rn(d, dc);
+            if (d < best || (d == best && c.k < best_k)) { best = d; best_k = c.k; best_slot = i; }
+        }
+    }
+    if (n_total > MAX_CAND) {
+        // pathological crowding: the shared list overflowed; finish with the exhaustive scan
+        // over all centres (same arithmetic, same tie break) so the result stays exact
         if (live) {
-            const int n = n_cand;
-            for (int i = 0; i < n; ++i) {
-                const Cand &c = cand[i];
-                if (y < c.y0 || y >= c.y1 || x < c.x0 || x >= c.x1) continue;
-                double dy = __dadd_rn(c.cy, -(double)y); dy = __dmul_rn(dy, dy);
-                double dx = __dadd_rn(c.cx, -(double)x); dx = __dmul_rn(dx, dx);
+            for (long k = 0; k < K; ++k) {
+                const double cy = s.cent[5 * k], cx = s.cent[5 * k + 1];
+                if (!(cy == cy) || !(cx == cx)) continue;
+                double lo;
+                lo = cy - two_s;       const int y0 = (int)(lo > 0.0 ? lo : 0.0);
+                lo = cy + two_s + 1.0; const int y1 = (int)(lo < (double)H ? lo : (double)H);
+                lo = cx - two_s;       const int x0 = (int)(lo > 0.0 ? lo : 0.0);
+                lo = cx + two_s + 1.0; const int x1 = (int)(lo < (double)W ? lo : (double)W);
+                if (y < y0 || y >= y1 || x < x0 || x >= x1) continue;
+                double dy = __dadd_rn(cy, -(double)y); dy = __dmul_rn(dy, dy);
+                double dx = __dadd_rn(cx, -(double)x); dx = __dmul_rn(dx, dx);
                 double d = __dmul_rn(__dadd_rn(dy, dx), spatial_weight);
-                double t = __dadd_rn(pl, -c.l);
-                double dc = __dmul_rn(t, t);                       // 0 + t*t
-                t = __dadd_rn(pa, -c.a); dc = __dadd_rn(dc, __dmul_rn(t, t));
-                t = __dadd_rn(pb, -c.b); dc = __dadd_rn(dc, __dmul_rn(t, t));
+                double t = __dadd_rn(pl, -s.cent[5 * k + 2]);
+                double dc = __dmul_rn(t, t);
+                t = __dadd_rn(pa, -s.cent[5 * k + 3]); dc = __dadd_rn(dc, __dmul_rn(t, t));
+                t = __dadd_rn(pb, -s.cent[5 * k + 4]); dc = __dadd_rn(dc, __dmul_rn(t, t));
                 d = __dadd_rn(d, dc);
-                if (d < best || (d == best && c.k < best_k)) { best = d; best_k = c.k; }
+                if (d < best || (d == best && (int)k < best_k)) { best = d; best_k = (int)k; best_slot = -1; }
             }
         }
     }
+    // ---- accumulate the new cluster sums ---------------------------------------
     if (live) {
         int k = best_k;
-        if (k >= 0) s.nearest[p] = k; else k = s.nearest[p];      // uncovered pixel keeps its previous cluster
-        atomicAdd(&s.acc_n[3 * k], 1ull);
-        atomicAdd(&s.acc_n[3 * k + 1], (u64)y);
-        atomicAdd(&s.acc_n[3 * k + 2], (u64)x);
-        atomicAdd(&s.acc_c[3 * k], pl);
-        atomicAdd(&s.acc_c[3 * k + 1], pa);
-        atomicAdd(&s.acc_c[3 * k + 2], pb);
+        if (k >= 0) s.nearest[p] = k; else { k = s.nearest[p]; best_slot = -1; }   // uncovered pixel keeps its previous cluster
+        if (best_slot >= 0) {
+            atomicAdd(&acc_n[best_slot][0], 1u);
+            atomicAdd(&acc_n[best_slot][1], (unsigned)y);
+            atomicAdd(&acc_n[best_slot][2], (unsigned)x);
+            atomicAdd(&acc_c[best_slot][0], pl);
+            atomicAdd(&acc_c[best_slot][1], pa);
+            atomicAdd(&acc_c[best_slot][2], pb);
+        } else {
+            atomicAdd(&s.acc_n[3 * k], 1ull);
+            atomicAdd(&s.acc_n[3 * k + 1], (u64)y);
+            atomicAdd(&s.acc_n[3 * k + 2], (u64)x);
+            atomicAdd(&s.acc_c[3 * k], pl);
+            atomicAdd(&s.acc_c[3 * k + 1], pa);
+            atomicAdd(&s.acc_c[3 * k + 2], pb);
+        }
     }
-}
-
-__global__ void slic_update_kernel(SlicWs s, long K) {
-    long k = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= K) return;
-    double n = (double)s.acc_n[3 * k];
-    // 0/0 -> NaN for an empty cluster, as in the sequential algorithm
-    s.cent[5 * k + 0] = __ddiv_rn((double)s.acc_n[3 * k + 1], n);
-    s.cent[5 * k + 1] = __ddiv_rn((double)s.acc_n[3 * k + 2], n);
-    s.cent[5 * k + 2] = __ddiv_rn(s.acc_c[3 * k], n);
-    s.cent[5 * k + 3] = __ddiv_rn(s.acc_c[3 * k + 1], n);
-    s.cent[5 * k + 4] = __ddiv_rn(s.acc_c[3 * k + 2], n);
-    s.acc_n[3 * k] = 0; s.acc_n[3 * k + 1] = 0; s.acc_n[3 * k + 2] = 0;
-    s.acc_c[3 * k] = 0.0; s.acc_c[3 * k + 1] = 0.0; s.acc_c[3 * k + 2] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+        if (acc_n[i][0] != 0u) {
+            const int k = cand[i].k;
+            atomicAdd(&s.acc_n[3 * k], (u64)acc_n[i][0]);
+            atomicAdd(&s.acc_n[3 * k + 1], (u64)acc_n[i][1]);
+            atomicAdd(&s.acc_n[3 * k + 2], (u64)acc_n[i][2]);
+            atomicAdd(&s.acc_c[3 * k], acc_c[i][0]);
+            atomicAdd(&s.acc_c[3 * k + 1], acc_c[i][1]);
+            atomicAdd(&s.acc_c[3 * k + 2], acc_c[i][2]);
+        }
+    }
+    // ---- the last block to finish updates the centres and re-bins them ---------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(s.ticket, 1u) == gridDim.x * gridDim.y - 1u) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const long cells = (long)s.cells_y * s.cells_x;
+    for (long i = tid; i < cells; i += 256) s.bin_count[i] = 0;
+    if (tid == 0) { *s.ov_count = 0; *s.ticket = 0u; }
+    __syncthreads();
+    for (long k = tid; k < K; k += 256) {
+        volatile u64 *an = s.acc_n + 3 * k;
+        volatile double *ac = s.acc_c + 3 * k;
+        const double cnt = (double)an[0];
+        // 0/0 -> NaN for an empty cluster, as in the sequential algorithm
+        const double cy = __ddiv_rn((double)an[1], cnt), cx = __ddiv_rn((double)an[2], cnt);
+        s.cent[5 * k + 0] = cy;
+        s.cent[5 * k + 1] = cx;
+        s.cent[5 * k + 2] = __ddiv_rn(ac[0], cnt);
+        s.cent[5 * k + 3] = __ddiv_rn(ac[1], cnt);
+        s.cent[5 * k + 4] = __ddiv_rn(ac[2], cnt);
+        an[0] = 0; an[1] = 0; an[2] = 0;
+        ac[0] = 0.0; ac[1] = 0.0; ac[2] = 0.0;
+        bin_insert(s, (int)k, cy, cx, step);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -234,10 +354,6 @@ __device__ __forceinline__ void uf_union(int32_t *parent, int a, int b) {
     }
 }
 
-__global__ void ccl_init_kernel(SlicWs s, long HW) {
-    long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < HW) { s.parent[p] = (int)p; s.size[p] = 0; s.seen[p] = 0; s.adj_root[p] = -1; }
-}
 __global__ void ccl_merge_kernel(SlicWs s, int H, int W) {
     long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (long)H * W) return;
@@ -390,7 +506,9 @@ extern "C" size_t wesup_slic_workspace_bytes(int H, int W, int n_segments) {
     int step, start, ny, nx;
     long K = slic_grid(H, W, n_segments, &step, &start, &ny, &nx);
     if (K <= 0) return 0;
-    return slic_ws_bytes((long)H * W, K);
+    int cy, cx;
+    long cells = n_cells(H, W, step, &cy, &cx);
+    return slic_ws_bytes((long)H * W, K, cells);
 }
 
 extern "C" int wesup_slic(const float *rgb, int rgb_layout, int H, int W, int n_segments, double compactness,
@@ -406,25 +524,27 @@ extern "C" int wesup_slic(const float *rgb, int rgb_layout, int H, int W, int n_
     long K = slic_grid(H, W, n_segments, &step, &start, &ny, &nx);
     WESUP_REQUIRE(K > 0, WESUP_E_UNSUPPORTED, "wesup_slic: degenerate seed grid for %dx%d / %d segments", H, W, n_segments);
     const long HW = (long)H * W;
-    SlicWs s = carve_slic(ws, HW, K);
+    int cells_y, cells_x;
+    const long cells = n_cells(H, W, step, &cells_y, &cells_x);
+    SlicWs s = carve_slic(ws, HW, K, cells);
+    s.cells_y = cells_y; s.cells_x = cells_x;
     const int nb = cdiv(HW, 256);
+    cudaError_t me = cudaMemsetAsync(s.acc_n, 0, s.zero_bytes, stream);
+    WESUP_REQUIRE(me == cudaSuccess, (int)me, "wesup_slic: memset: %s", cudaGetErrorString(me));
     slic_lab_kernel<<<nb, 256, 0, stream>>>(rgb, rgb_layout, HW, 1.0 / compactness, s.lab);
     slic_init_kernel<<<cdiv(HW > K ? HW : K, 256), 256, 0, stream>>>(s, K, nx, step, start, HW);
     float stepf = (float)step;
     double spatial_weight = 1.0 / (double)(stepf * stepf);
     dim3 tiles(cdiv(W, AT), cdiv(H, AT));
-    for (int it = 0; it < max_iter; ++it) {
-        slic_assign_kernel<<<tiles, 256, 0, stream>>>(s, H, W, K, step, spatial_weight);
-        slic_update_kernel<<<cdiv(K, 256), 256, 0, stream>>>(s, K);
-    }
+    for (int it = 0; it < max_iter; ++it)
+        slic_sweep_kernel<<<tiles, 256, 0, stream>>>(s, H, W, K, step, spatial_weight);
     if (!enforce_connectivity) {
         copy_labels_kernel<<<nb, 256, 0, stream>>>(s.nearest, labels, HW, n_labels, (int)K);
-        WESUP_CHECK_LAUNCH("wesup_slic", 3 + 2 * max_iter);
+        WESUP_CHECK_LAUNCH("wesup_slic", 3 + max_iter);
         return 0;
     }
     double segment_size = (double)HW / (double)n_segments;
     int min_size = (int)(0.5 * segment_size);
-    ccl_init_kernel<<<nb, 256, 0, stream>>>(s, HW);
     ccl_merge_kernel<<<nb, 256, 0, stream>>>(s, H, W);
     ccl_flatten_kernel<<<nb, 256, 0, stream>>>(s, HW);
     ccl_flags_kernel<<<nb, 256, 0, stream>>>(s, HW, min_size);
@@ -432,6 +552,6 @@ extern "C" int wesup_slic(const float *rgb, int rgb_layout, int H, int W, int n_
     device_exclusive_scan(s.small_scan, HW, s.block_sums, nullptr, stream);
     ccl_small_adjacent_kernel<<<nb, 256, 0, stream>>>(s, H, W, min_size);
     ccl_relabel_kernel<<<nb, 256, 0, stream>>>(s, HW, min_size, labels);
-    WESUP_CHECK_LAUNCH("wesup_slic", 2 + 2 * max_iter + 12);
+    WESUP_CHECK_LAUNCH("wesup_slic", 2 + max_iter + 11);
     return 0;
 }

@@ -68,6 +68,9 @@ class BaseTrainer(ABC):
     def preprocess(self, *data):
         return [datum.to(self.device) for datum in data]
 
+    def prefetch(self, *data):
+        """Hook: start preprocessing `data` ahead of time (no-op by default)."""
+
     @abstractmethod
     def compute_loss(self, pred, target, metrics=None):
         ...
@@ -110,25 +113,46 @@ class BaseTrainer(ABC):
 
     # ---- the loop -------------------------------------------------------------
     def train_one_iteration(self, phase, *data):
+        """Same sequence as the reference (models/base.py:184-211): preprocess, zero_grad,
+        forward, loss, NaN check, backward, step, postprocess, metrics.  The host reads
+        every scalar of the iteration (loss, loss-side metrics, accuracy/dice) in ONE
+        device-to-host transfer after the optimizer step has been enqueued, so the GPU
+        never idles behind a `.item()`; a NaN loss still raises ValueError('Loss is nan!')
+        in the same iteration (uncaught by the epoch loop, as in the reference)."""
         input_, target = self.preprocess(*data)
         if self.grad_sync is not None:
             self.grad_sync.zero_grad()       # keeps .grad as views of the flat all-reduce buffer
         else:
             self.optimizer.zero_grad()
         metrics = {}
-        with torch.set_grad_enabled(phase == "train"):
-            pred = self.model(input_)
-            if phase == "train":
-                loss = self.compute_loss(pred, target, metrics=metrics)
-                if torch.isnan(loss):
-                    raise ValueError("Loss is nan!")
-                metrics["loss"] = loss.item()
-                loss.backward()
-                if self.grad_sync is not None:
-                    self.grad_sync.average_gradients()
-                self.optimizer.step()
-        pred, target = self.postprocess(pred, target)
-        self.tracker.step({**metrics, **self.evaluate(pred, target)})
+        self._defer_scalars = True
+        try:
+            with torch.set_grad_enabled(phase == "train"):
+                pred = self.model(input_)
+                if phase == "train":
+                    loss = self.compute_loss(pred, target, metrics=metrics)
+                    metrics["loss"] = loss.detach()
+                    loss.backward()
+                    if self.grad_sync is not None:
+                        self.grad_sync.average_gradients()
+                    self.optimizer.step()
+            pred, target = self.postprocess(pred, target)
+            metrics.update(self.evaluate(pred, target))
+        finally:
+            self._defer_scalars = False
+        metrics = self._read_scalars(metrics)
+        if phase == "train" and metrics["loss"] != metrics["loss"]:
+            raise ValueError("Loss is nan!")
+        self.tracker.step(metrics)
+
+    @staticmethod
+    def _read_scalars(metrics):
+        """Replace every 0-dim device tensor in `metrics` by its float with one transfer."""
+        keys = [k for k, v in metrics.items() if torch.is_tensor(v)]
+        if keys:
+            vals = torch.stack([metrics[k].detach().float().reshape(()) for k in keys]).tolist()
+            metrics = {**metrics, **dict(zip(keys, vals))}
+        return metrics
 
     def train_one_epoch(self, no_val=False):
         for phase in (["train"] if no_val else ["train", "val"]):
@@ -140,11 +164,17 @@ class BaseTrainer(ABC):
             else:
                 self.model.eval()
                 self.tracker.eval()
-            for data in self.dataloaders[phase]:
+            batches = iter(self.dataloaders[phase])
+            data = next(batches, None)
+            while data is not None:
+                upcoming = next(batches, None)
                 try:
+                    if upcoming is not None and self.kwargs.get("prefetch", True):
+                        self.prefetch(*upcoming)         # next image's preprocessing overlaps this iteration
                     self.train_one_iteration(phase, *data)
                 except RuntimeError as ex:       # same policy as the reference (base.py:234-237)
                     self.logger.exception(ex)
+                data = upcoming
             self.logger.info(f"Took {time.time() - start:.2f}s.")
             self.logger.info(self.tracker.log())
 
@@ -196,8 +226,13 @@ class BaseTrainer(ABC):
     def evaluate(self, pred, target=None, verbose=False):
         if target is None:
             return {}
+        lazy = getattr(self, "_defer_scalars", False)
         scores = defaultdict(list)
         for P, G in zip(pred, target):
             for func in self.metric_funcs:
-                scores[func.__name__].append(func(P, G))
-        return {k: np.mean(v) for k, v in scores.items()}
+                deferred = getattr(func, "deferred", None) if lazy else None
+                scores[func.__name__].append(deferred(P, G) if deferred is not None else func(P, G))
+        out = {}
+        for k, v in scores.items():
+            out[k] = torch.stack(v).mean() if torch.is_tensor(v[0]) else np.mean(v)
+        return out

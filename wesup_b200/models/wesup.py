@@ -51,7 +51,7 @@ def _vgg16_features(pretrained: bool) -> nn.Sequential:
 # ---------------------------------------------------------------------------
 # module-level functions (reference: models/wesup.py:18-139)
 # ---------------------------------------------------------------------------
-def _preprocess_superpixels(segments, mask=None, epsilon=1e-7, dense=False, n_sp=None):
+def _preprocess_superpixels(segments, mask=None, epsilon=1e-7, dense=False, n_sp=None, n_sp_dev=None):
     """Superpixel rows + labels from a SLIC label map (reference :18-63).
 
     Returns `(sp_maps, sp_labels)`.  `sp_maps` is a compact `SuperpixelMaps`
@@ -60,10 +60,11 @@ def _preprocess_superpixels(segments, mask=None, epsilon=1e-7, dense=False, n_sp
     split and the multi-hot quantisation are bit-identical to the reference.
     `epsilon` only guards a division whose result is compared with zero / with
     the row maximum in the reference, so integer class counts are equivalent.
+    `n_sp` / `n_sp_dev`: see `SuperpixelMaps.from_labels` (one host sync in total).
     """
     if mask is not None and is_empty_tensor(mask):
         mask = None
-    sp = SuperpixelMaps.from_labels(segments, mask, n_sp=n_sp)
+    sp = SuperpixelMaps.from_labels(segments, mask, n_sp=n_sp, n_sp_dev=n_sp_dev)
     sp_labels = sp.sp_labels if mask is not None else empty_tensor().to(segments.device)
     return (sp.to_dense() if dense else sp), sp_labels
 
@@ -238,15 +239,22 @@ class WESUPTrainer(BaseTrainer):
             lr=5e-5, momentum=self.kwargs.get("momentum"), weight_decay=self.kwargs.get("weight_decay"))
         return optimizer, None      # the reference builds a scheduler and discards it (:452-455)
 
-    def segment(self, img):
+    def segment(self, img, sync=True):
         """GPU SLIC with the reference's parameters (:471-476).  Returns the int32
-        label map and the number of labels (one host sync, like the reference's
-        `.cpu()` round trip but without moving the image)."""
+        label map and the number of labels -- as a host int (one sync, like the
+        reference's `.cpu()` round trip but without moving the image) or, with
+        `sync=False`, as `(device scalar, host upper bound)`."""
         n_segments = int(img.size(-2) * img.size(-1) / self.kwargs.get("sp_area"))
         labels, n_labels = ops.slic(img, n_segments=n_segments, compactness=self.kwargs.get("sp_compactness"))
-        return labels, int(n_labels.item())
+        if sync:
+            return labels, int(n_labels.item())
+        # every kept component has >= min_size = int(0.5 * HW / n_segments) pixels (skimage's rule)
+        hw = img.size(-2) * img.size(-1)
+        bound = hw // max(int(0.5 * hw / n_segments), 1) + 1
+        return labels, (n_labels, bound)
 
-    def preprocess(self, *data):
+    def _enqueue_preprocess(self, *data):
+        """Everything `preprocess` does up to (not including) its single host wait."""
         data = [datum.to(self.device, non_blocking=True) for datum in data]
         if len(data) == 3:
             img, pixel_mask, point_mask = data
@@ -259,15 +267,58 @@ class WESUPTrainer(BaseTrainer):
             pixel_mask = empty_tensor()
         else:
             raise ValueError("Invalid input data for WESUP")
-        segments, n_sp = self.segment(img)
+        segments, (n_dev, bound) = self.segment(img, sync=False)
         if point_mask is not None and not is_empty_tensor(point_mask):
             mask = point_mask.squeeze(0) if point_mask.dim() == 4 else point_mask.squeeze()
         elif pixel_mask is not None and not is_empty_tensor(pixel_mask):
             mask = pixel_mask.squeeze(0) if pixel_mask.dim() == 4 else pixel_mask.squeeze()
         else:
             mask = None
-        sp_maps, sp_labels = _preprocess_superpixels(segments, mask, epsilon=self.kwargs.get("epsilon"), n_sp=n_sp)
+        # SLIC -> statistics without a host round trip in between: ONE host wait per image
+        pending = SuperpixelMaps.from_labels(segments, None if mask is None else mask, n_sp=bound, n_sp_dev=n_dev, defer=True)
+        return img, pixel_mask, mask is not None, pending
+
+    @staticmethod
+    def _finish_preprocess(img, pixel_mask, has_mask, pending):
+        sp_maps = pending.finish()
+        sp_labels = sp_maps.sp_labels if has_mask else empty_tensor().to(img.device)
         return (img, sp_maps), (pixel_mask, sp_labels)
+
+    def preprocess(self, *data):
+        staged_map = getattr(self, "_prefetched", None)
+        hit = staged_map.pop(tuple(id(t) for t in data), None) if staged_map else None
+        if hit is not None and all(a is b for a, b in zip(hit[0], data)):
+            _, staged, done = hit
+            torch.cuda.current_stream(self.device).wait_event(done)
+            return self._finish_preprocess(*staged)
+        return self._finish_preprocess(*self._enqueue_preprocess(*data))
+
+    def prefetch(self, *data):
+        """Run `preprocess(*data)` (H2D copy, GPU SLIC, superpixel statistics) on a side
+        stream, ahead of the training stream.  A later `preprocess` call with these same
+        tensor objects picks the result up; its host scalars are usually already there."""
+        if not torch.cuda.is_available():
+            return
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=self.device)
+            self._prefetched = {}
+        key = tuple(id(t) for t in data)
+        if key in self._prefetched:
+            return
+        while len(self._prefetched) >= 4:                  # bounded look-ahead
+            self._prefetched.pop(next(iter(self._prefetched)))
+        main = torch.cuda.current_stream(self.device)
+        side = self._side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            staged = self._enqueue_preprocess(*data)
+            done = torch.cuda.Event()
+            done.record(side)
+        img, pixel_mask, _, pending = staged
+        for t in [img, pixel_mask] + pending.tensors():      # allocated on `side`, consumed on `main`
+            if torch.is_tensor(t) and t.is_cuda:
+                t.record_stream(main)
+        self._prefetched[key] = (tuple(data), staged, done)
 
     def compute_loss(self, pred, target, metrics=None):
         _, sp_labels = target
@@ -287,8 +338,11 @@ class WESUPTrainer(BaseTrainer):
             if metrics is not None and isinstance(metrics, dict):
                 metrics["labeled_sp_ratio"] = labeled_num / total_num
                 if self.kwargs.get("enable_propagation"):
-                    metrics["propagated_labels"] = propagated_labels.sum().item()
-                    metrics["propagate_loss"] = propagate_loss.item()
+                    # inside train_one_iteration the scalars stay on the device and are read
+                    # in one transfer at the end of the iteration; direct callers get floats
+                    lazy = getattr(self, "_defer_scalars", False)
+                    metrics["propagated_labels"] = propagated_labels.sum() if lazy else propagated_labels.sum().item()
+                    metrics["propagate_loss"] = propagate_loss.detach() if lazy else propagate_loss.item()
         else:                                # fully-supervised mode
             loss = self.xentropy(sp_pred, sp_labels)
         self.model.sp_pred = None            # clear outdated prediction (:529)

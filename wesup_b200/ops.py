@@ -101,8 +101,18 @@ class SuperpixelMaps:
 
     # -- constructors ----------------------------------------------------------
     @staticmethod
-    def from_labels(labels: torch.Tensor, mask: Optional[torch.Tensor] = None, n_sp: Optional[int] = None) -> "SuperpixelMaps":
-        """labels: (H,W) integer ids in [0,n_sp); mask: (C,H,W) int64 one-hot-or-zero or None."""
+    def from_labels(labels: torch.Tensor, mask: Optional[torch.Tensor] = None, n_sp: Optional[int] = None,
+                    n_sp_dev: Optional[torch.Tensor] = None, defer: bool = False) -> "SuperpixelMaps":
+        """labels: (H,W) integer ids in [0,n_sp); mask: (C,H,W) int64 one-hot-or-zero or None.
+
+        `n_sp_dev` (a 1-element device tensor holding the true number of ids, e.g. the
+        `n_labels` output of `ops.slic`) turns `n_sp` into an UPPER BOUND: the statistics
+        run over the bound (absent ids are empty superpixels that sort to the very end of
+        the row order), then the true count and the labeled count come back in ONE
+        device-to-host read and every per-row array is trimmed to the true count.
+        With `defer=True` that read is only *started* (async copy into pinned memory) and a
+        `PendingSuperpixelMaps` is returned; `.finish()` completes it later, so a caller can
+        run this on a side stream one image ahead without ever stalling the main stream."""
         _require_cuda(labels, "segments")
         if labels.dim() != 2:
             raise ValueError("segments must be (H, W)")
@@ -119,11 +129,11 @@ class SuperpixelMaps:
             mask64 = mask.to(device=dev, dtype=torch.int64).contiguous()
             n_cls = mask64.size(0)
         i32 = dict(dtype=torch.int32, device=dev)
-        order = torch.empty(n_sp, **i32)
-        row_labels = torch.empty(h * w, **i32)
-        counts = torch.empty(n_sp, **i32)
-        seg_offsets = torch.empty(n_sp + 1, **i32)
-        seg_pixels = torch.empty(h * w, **i32)
+        # one allocation for the three per-row int arrays, one for the two per-pixel ones
+        rows = torch.empty(3 * n_sp + 1, **i32)
+        order, counts, seg_offsets = rows[:n_sp], rows[n_sp:2 * n_sp], rows[2 * n_sp:]
+        px = torch.empty(2 * h * w, **i32)
+        row_labels, seg_pixels = px[:h * w], px[h * w:]
         n_labeled = torch.zeros(1, **i32)
         sp_labels = torch.empty(n_sp, n_cls, dtype=torch.float32, device=dev) if n_cls else None
         lib = _lib.load()
@@ -132,8 +142,12 @@ class SuperpixelMaps:
                                  order.data_ptr(), row_labels.data_ptr(), counts.data_ptr(), seg_offsets.data_ptr(),
                                  seg_pixels.data_ptr(), sp_labels.data_ptr() if sp_labels is not None else None,
                                  n_labeled.data_ptr(), ws.data_ptr(), _stream()), "wesup_sp_stats")
-        return SuperpixelMaps(h, w, n_sp, order, row_labels, counts, seg_offsets, seg_pixels, sp_labels,
-                              n_labeled if n_cls else None)
+        sp = SuperpixelMaps(h, w, n_sp, order, row_labels, counts, seg_offsets, seg_pixels, sp_labels,
+                            n_labeled if n_cls else None)
+        if n_sp_dev is None:
+            return sp
+        pending = PendingSuperpixelMaps(sp, torch.cat([n_sp_dev.reshape(1).to(torch.int32), n_labeled]), bool(n_cls))
+        return pending if defer else pending.finish()
 
     @staticmethod
     def from_dense(sp_maps: torch.Tensor) -> "SuperpixelMaps":
@@ -142,6 +156,36 @@ class SuperpixelMaps:
         _require_cuda(sp_maps, "sp_maps")
         owner = sp_maps.argmax(dim=0)
         return SuperpixelMaps.from_labels(owner, None, n_sp=sp_maps.size(0))
+
+
+class PendingSuperpixelMaps:
+    """`SuperpixelMaps` built over an upper bound of the superpixel count whose two
+    host scalars (true count, labeled count) are still in flight."""
+
+    def __init__(self, sp: SuperpixelMaps, scalars_dev: torch.Tensor, has_labels: bool):
+        self.sp, self.has_labels = sp, has_labels
+        self.host = torch.empty(2, dtype=torch.int32, pin_memory=True)
+        self.host.copy_(scalars_dev, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record(torch.cuda.current_stream(scalars_dev.device))
+
+    def tensors(self):
+        sp = self.sp
+        return [t for t in (sp.order, sp.row_labels, sp.counts, sp.seg_offsets, sp.seg_pixels, sp.sp_labels_full,
+                            sp._n_labeled_dev) if t is not None]
+
+    def finish(self) -> SuperpixelMaps:
+        self.event.synchronize()                               # the one host wait per image
+        n_true, n_labeled = self.host.tolist()
+        sp = self.sp
+        if n_true > sp.n:
+            raise RuntimeError(f"superpixel count {n_true} exceeds the bound {sp.n} the statistics ran with")
+        sp.order, sp.counts, sp.seg_offsets = sp.order[:n_true], sp.counts[:n_true], sp.seg_offsets[:n_true + 1]
+        if sp.sp_labels_full is not None:
+            sp.sp_labels_full = sp.sp_labels_full[:n_true]
+        sp.n = n_true
+        sp._n_labeled = int(n_labeled) if self.has_labels else 0
+        return sp
 
 
 # ---------------------------------------------------------------------------
@@ -314,9 +358,16 @@ def paint(sp: SuperpixelMaps, sp_pred: torch.Tensor, cls: int = 1) -> torch.Tens
 # ---------------------------------------------------------------------------
 # (c) label propagation
 # ---------------------------------------------------------------------------
-def label_propagate(features: torch.Tensor, y_l: torch.Tensor, threshold: float = 0.95, return_aux: bool = False):
+_LP_ALGOS = {"auto": "wesup_label_propagate", "exact": "wesup_label_propagate_exact", "tc": "wesup_label_propagate_tc"}
+
+
+def label_propagate(features: torch.Tensor, y_l: torch.Tensor, threshold: float = 0.95, return_aux: bool = False,
+                    algo: str = "auto", return_stats: bool = False):
     """Fused distance -> similarity -> arg-max -> threshold -> label copy
-    (/root/reference/models/wesup.py:99-139).  Returns y_u (n_u, C) [, src, max_sim]."""
+    (/root/reference/models/wesup.py:99-139).  Returns y_u (n_u, C) [, src, max_sim].
+    algo: 'auto' (library dispatch), 'exact' (CUDA cores) or 'tc' (tcgen05 filter +
+    exact re-evaluation; D must be 32); all three give bit-identical results.
+    return_stats (tc only): also return {'exact_evals', 'max_err_ratio'} (syncs)."""
     lib = _lib.load()
     features = features.detach().contiguous().float()
     y_l = y_l.detach().contiguous().float()
@@ -328,14 +379,24 @@ def label_propagate(features: torch.Tensor, y_l: torch.Tensor, threshold: float 
     y_u = torch.zeros((n_u, n_cls), dtype=torch.float32, device=dev)
     src = torch.zeros(n_u, dtype=torch.int32, device=dev)
     sim = torch.zeros(n_u, dtype=torch.float32, device=dev)
+    stats = None
     if n_u > 0 and n_l > 0:
         ws = _ws(lib.wesup_label_propagate_workspace_bytes(n, d, n_l), dev)
-        check(lib.wesup_label_propagate(features.data_ptr(), n, d, n_l, y_l.data_ptr(), n_cls, float(threshold),
-                                        y_u.data_ptr(), src.data_ptr(), sim.data_ptr(), ws.data_ptr(), _stream()),
-              "wesup_label_propagate")
-    if return_aux:
-        return y_u, src, sim
-    return y_u
+        name = _LP_ALGOS[algo]
+        check(getattr(lib, name)(features.data_ptr(), n, d, n_l, y_l.data_ptr(), n_cls, float(threshold),
+                                 y_u.data_ptr(), src.data_ptr(), sim.data_ptr(), ws.data_ptr(), _stream()), name)
+        if return_stats and algo == "tc":
+            import ctypes
+            import struct
+            torch.cuda.current_stream().synchronize()
+            out = (ctypes.c_ulonglong * 2)()
+            check(lib.wesup_label_propagate_tc_stats(ws.data_ptr(), n, n_l, out), "wesup_label_propagate_tc_stats")
+            stats = {"exact_evals": int(out[0]), "pairs": n_u * n_l,
+                     "max_err_ratio": struct.unpack("f", struct.pack("I", int(out[1]) & 0xFFFFFFFF))[0]}
+    result = (y_u, src, sim) if return_aux else (y_u,)
+    if return_stats:
+        result = result + (stats,)
+    return result if len(result) > 1 else result[0]
 
 
 # ---------------------------------------------------------------------------
