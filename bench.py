@@ -207,8 +207,9 @@ def kernel_rooflines(dev, peak_gbs):
         Cs, hs, ws_ = [s.size(1) for s in sides], [s.size(2) for s in sides], [s.size(3) for s in sides]
         ptrs = ops._lib.ptr_array([t.data_ptr() for t in gsides])
         ia = ops._lib.int_array
-        ms = time_kernel(lambda: lib.wesup_hypercolumn_bwd(gf.data_ptr(), code, 1, ia(Cs), ia(hs), ia(ws_), 13, H, W, ptrs, st),
-                         5, flush)
+        hws = torch.empty(lib.wesup_hypercolumn_bwd_workspace_bytes(ia(Cs), ia(hs), ia(ws_), 13, H, W), dtype=torch.uint8, device=dev)
+        ms = time_kernel(lambda: lib.wesup_hypercolumn_bwd(gf.data_ptr(), code, 1, ia(Cs), ia(hs), ia(ws_), 13, H, W, ptrs,
+                                                           hws.data_ptr(), st), 5, flush)
         b = side_bytes + C_HYPER * hw * es
         out[f"hypercolumn_bwd_{tag}"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
         if dtype == torch.float32:

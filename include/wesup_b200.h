@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define WESUP_ABI_VERSION 2
+#define WESUP_ABI_VERSION 3
 #define WESUP_MAX_LEVELS 16
 
 /* element type of the hypercolumn tensor */
@@ -62,10 +62,15 @@ int wesup_hypercolumn_fwd(const void *const *side, const int *C, const int *h, c
                           void *stream);
 /* adjoint of the above (what autograd derives for models/wesup.py:254-261):
  * grad_side[l] (fp32, same layout as side[l]) = bilinear^T of the level's
- * channel slice of grad_out.  Deterministic (gather form, no atomics). */
+ * channel slice of grad_out.  Deterministic (no atomics).  `ws` (size from
+ * wesup_hypercolumn_bwd_workspace_bytes) enables the separable two-pass kernels
+ * that stream grad_out once (WESUP_HWC); with ws == NULL, or for WESUP_CHW, the
+ * single-pass gather kernels run. */
+size_t wesup_hypercolumn_bwd_workspace_bytes(const int *C, const int *h, const int *w, int n_levels,
+                                             int H, int W);
 int wesup_hypercolumn_bwd(const void *grad_out, int grad_dtype, int layout, const int *C,
                           const int *h, const int *w, int n_levels, int H, int W,
-                          void *const *grad_side, void *stream);
+                          void *const *grad_side, void *ws, void *stream);
 
 /* ---- superpixel statistics: replaces _preprocess_superpixels ---------------
  * (models/wesup.py:18-63) without the dense (N,H,W) maps.

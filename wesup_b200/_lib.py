@@ -11,7 +11,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "libwesup_b200.so"
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 F32, BF16 = 0, 1
 CHW, HWC = 0, 1
@@ -25,7 +25,8 @@ SIGNATURES = {
     "wesup_last_error": (c_char_p, []),
     "wesup_kernel_launches": (ctypes.c_ulonglong, []),
     "wesup_hypercolumn_fwd": (c_int, [POINTER(_vp), _ip, _ip, _ip, c_int, c_int, c_int, _vp, c_int, c_int, _vp]),
-    "wesup_hypercolumn_bwd": (c_int, [_vp, c_int, c_int, _ip, _ip, _ip, c_int, c_int, c_int, POINTER(_vp), _vp]),
+    "wesup_hypercolumn_bwd_workspace_bytes": (c_size_t, [_ip, _ip, _ip, c_int, c_int, c_int]),
+    "wesup_hypercolumn_bwd": (c_int, [_vp, c_int, c_int, _ip, _ip, _ip, c_int, c_int, c_int, POINTER(_vp), _vp, _vp]),
     "wesup_sp_stats_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "wesup_sp_stats": (c_int, [_vp, _vp, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wesup_sp_pool_fwd": (c_int, [_vp, c_int, c_int, _vp, _vp, c_int, c_int, c_int, _vp, _vp]),

@@ -521,6 +521,159 @@ __global__ void __launch_bounds__(256) hyper_bwd_chw_kernel(const Levels L, cons
     L.dst[l][idx] = acc;
 }
 
+// ---------------------------------------------------------------------------
+// backward, pixel-major, separable two-pass form (the fast path when the caller
+// provides a workspace).  Pass 1 streams grad_out exactly once: block = one
+// output row x a slice of the channel groups, thread = one 16-byte channel
+// group walking along x with the two live low-res column accumulators in
+// registers; a finished column is written once to R[l][y][j][c] (identity
+// levels go straight to their gradient).  Pass 2 reduces R over the <= 2/scale+2
+// output rows of each low-res row.  Deterministic (fixed order, no atomics);
+// extra traffic = write + read of R (sum_l H*w_l*C_l*4 bytes, 0.32 GB at 464^2)
+// on top of the 1.82 GB that must be read anyway.
+// ---------------------------------------------------------------------------
+// The per-level row partials R[l] (H, w_l, C_l) fp32 live in the workspace; their pointers
+// travel in Levels::src (unused by the backward otherwise) so that the kernels keep a
+// single parameter struct (a second dynamically indexed struct is copied to local memory).
+template <int V> __device__ __forceinline__ FVec<V> ld_grad(const float *p) {
+    FVec<V> r;
+#pragma unroll
+    for (int k = 0; k < V / 4; ++k) {
+        float4 t = ldg_stream(reinterpret_cast<const float4 *>(p) + k);
+        r.v[4 * k] = t.x; r.v[4 * k + 1] = t.y; r.v[4 * k + 2] = t.z; r.v[4 * k + 3] = t.w;
+    }
+    return r;
+}
+template <int V> __device__ __forceinline__ FVec<V> ld_grad(const __nv_bfloat16 *p) {
+    FVec<V> r;
+#pragma unroll
+    for (int k = 0; k < V / 4; ++k) {
+        float4 t = unpack_bf16x4(ldg_stream(reinterpret_cast<const uint2 *>(p) + k));
+        r.v[4 * k] = t.x; r.v[4 * k + 1] = t.y; r.v[4 * k + 2] = t.z; r.v[4 * k + 3] = t.w;
+    }
+    return r;
+}
+__device__ __forceinline__ void st_f4(float *p, const FVec<4> &a) {
+    *reinterpret_cast<float4 *>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(160, 4) hyper_bwd_rows_kernel(const Levels L, const T *__restrict__ grad_out, int groups_per_block) {
+    constexpr int V = 4;
+    const int g = blockIdx.y * groups_per_block + threadIdx.x;
+    if (threadIdx.x >= groups_per_block || g * V >= L.Ctot) return;
+    const int c = g * V;
+    int l = 0;
+    while (l + 1 < L.n && c >= L.coff[l + 1]) ++l;
+    const int Cl = L.C[l], hl = L.h[l], wl = L.w[l], cl = c - L.coff[l];
+    const int y = blockIdx.x, W = L.W;
+    const T *__restrict__ gin = grad_out + (long)y * W * L.Ctot + c;
+    const long gstride = L.Ctot;
+    if (hl == L.H && wl == W) {                        // identity level: the gradient is a copy
+        float *d = L.dst[l] + (long)y * wl * Cl + cl;
+        int x = 0;
+        for (; x + 4 <= W; x += 4) {
+            FVec<V> v0 = ld_grad<V>(gin + (long)x * gstride), v1 = ld_grad<V>(gin + (long)(x + 1) * gstride),
+                    v2 = ld_grad<V>(gin + (long)(x + 2) * gstride), v3 = ld_grad<V>(gin + (long)(x + 3) * gstride);
+            st_f4(d + (long)x * Cl, v0); st_f4(d + (long)(x + 1) * Cl, v1); st_f4(d + (long)(x + 2) * Cl, v2); st_f4(d + (long)(x + 3) * Cl, v3);
+        }
+        for (; x < W; ++x) st_f4(d + (long)x * Cl, ld_grad<V>(gin + (long)x * gstride));
+        return;
+    }
+    float *__restrict__ R = const_cast<float *>(L.src[l]) + (long)y * wl * Cl + cl;
+    const float sx = L.sx[l];
+    int cur = bilinear_tap(0, sx, wl).i0;
+    FVec<V> a0, a1;
+#pragma unroll
+    for (int k = 0; k < V; ++k) { a0.v[k] = 0.f; a1.v[k] = 0.f; }
+    auto step = [&](int x, const FVec<V> &gv) {
+        const Tap tx = bilinear_tap(x, sx, wl);
+        while (tx.i0 != cur) {                          // advance (by one for an upsample)
+            st_f4(R + (long)cur * Cl, a0);
+            a0 = a1;
+#pragma unroll
+            for (int k = 0; k < V; ++k) a1.v[k] = 0.f;
+            ++cur;
+        }
+        if (tx.i1 != tx.i0) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) { a0.v[k] = fmaf(tx.w0, gv.v[k], a0.v[k]); a1.v[k] = fmaf(tx.w1, gv.v[k], a1.v[k]); }
+        } else {
+            const float wsum = tx.w0 + tx.w1;
+#pragma unroll
+            for (int k = 0; k < V; ++k) a0.v[k] = fmaf(wsum, gv.v[k], a0.v[k]);
+        }
+    };
+    int x = 0;
+    for (; x + 8 <= W; x += 8) {                        // eight independent 16-byte loads in flight per thread
+        FVec<V> v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = ld_grad<V>(gin + (long)(x + u) * gstride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) step(x + u, v[u]);
+    }
+    for (; x < W; ++x) step(x, ld_grad<V>(gin + (long)x * gstride));
+    st_f4(R + (long)cur * Cl, a0);
+    for (int j = cur + 1; j < wl; ++j) {               // at most one more column carries weight
+        st_f4(R + (long)j * Cl, a1);
+#pragma unroll
+        for (int k = 0; k < V; ++k) a1.v[k] = 0.f;
+    }
+}
+
+// y-footprint tables for pass 2 (same fp32 tap arithmetic as the forward): for low-res row i of
+// level l, the first output row, the number of rows and their weights.  Pointers travel in
+// Levels::dst-adjacent fields would need a second struct; the tables are therefore packed behind
+// one base pointer with per-level offsets stored in Levels::ncol (row length K) / Levels::soff.
+__global__ void hyper_bwd_ytable_kernel(const Levels L, int32_t *__restrict__ tab) {
+    const int l = blockIdx.y;
+    const int hl = L.h[l];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hl || (hl == L.H && L.w[l] == L.W)) return;
+    const int K = L.ncol[l];
+    int32_t *base = tab + L.soff[l];                   // [hl] first, [hl] count, [hl*K] weights (float bits)
+    int lo, hi;
+    footprint(i, L.sy[l], L.H, lo, hi);
+    int first = -1, last = -2;
+    for (int d = lo; d <= hi; ++d) {
+        Tap t = bilinear_tap(d, L.sy[l], hl);
+        if (t.i0 == i || t.i1 == i) { if (first < 0) first = d; last = d; }
+    }
+    int n = first < 0 ? 0 : min(last - first + 1, K);
+    base[i] = first < 0 ? 0 : first;
+    base[hl + i] = n;
+    for (int k = 0; k < n; ++k) base[2 * hl + (long)i * K + k] = __float_as_int(tap_weight(first + k, i, L.sy[l], hl));
+}
+
+// pass 2: one thread per (non-identity level, low-res pixel, 4-channel group)
+__global__ void __launch_bounds__(256) hyper_bwd_cols_kernel(const Levels L, const int32_t *__restrict__ tab) {
+    const int l = blockIdx.y;
+    const int Cl = L.C[l], c4n = Cl >> 2, hl = L.h[l], wl = L.w[l];
+    if (hl == L.H && wl == L.W) return;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)hl * wl * c4n) return;
+    const int c = ((int)(idx % c4n)) << 2;
+    const long q = idx / c4n;
+    const int j = (int)(q % wl), i = (int)(q / wl);
+    const long rstride = (long)wl * Cl;
+    const int32_t *__restrict__ base = tab + L.soff[l];
+    const int y0 = __ldg(base + i), n = __ldg(base + hl + i);
+    const int32_t *__restrict__ wy = base + 2 * hl + (long)i * L.ncol[l];
+    const float *__restrict__ R = L.src[l] + (long)y0 * rstride + (long)j * Cl + c;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int k = 0;
+    for (; k + 4 <= n; k += 4) {                        // four independent row loads in flight
+        float4 r0 = __ldg(reinterpret_cast<const float4 *>(R + (long)k * rstride));
+        float4 r1 = __ldg(reinterpret_cast<const float4 *>(R + (long)(k + 1) * rstride));
+        float4 r2 = __ldg(reinterpret_cast<const float4 *>(R + (long)(k + 2) * rstride));
+        float4 r3 = __ldg(reinterpret_cast<const float4 *>(R + (long)(k + 3) * rstride));
+        fma4(acc, __int_as_float(__ldg(wy + k)), r0); fma4(acc, __int_as_float(__ldg(wy + k + 1)), r1);
+        fma4(acc, __int_as_float(__ldg(wy + k + 2)), r2); fma4(acc, __int_as_float(__ldg(wy + k + 3)), r3);
+    }
+    for (; k < n; ++k) fma4(acc, __int_as_float(__ldg(wy + k)), __ldg(reinterpret_cast<const float4 *>(R + (long)k * rstride)));
+    *reinterpret_cast<float4 *>(L.dst[l] + ((long)i * wl + j) * Cl + c) = acc;
+}
+
 static int fill_levels(Levels &L, const char *who, const int *C, const int *h, const int *w, int n_levels, int H, int W,
                        int layout) {
     WESUP_REQUIRE(C && h && w, WESUP_E_ARG, "%s: null geometry", who);
@@ -624,8 +777,29 @@ extern "C" int wesup_hypercolumn_fwd(const void *const *side, const int *C, cons
     return 0;
 }
 
+static inline int ytable_len(int hl, int H) {
+    float scale = bilinear_scale(hl, H);
+    if (!(scale > 0.f)) return H;
+    int k = (int)(2.0f / scale) + 7;
+    return k < H + 2 ? k : H + 2;
+}
+
+extern "C" size_t wesup_hypercolumn_bwd_workspace_bytes(const int *C, const int *h, const int *w, int n_levels, int H, int W) {
+    if (!C || !h || !w || n_levels <= 0 || n_levels > WESUP_MAX_LEVELS || H <= 0 || W <= 0) return 0;
+    size_t total = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        if (C[l] <= 0 || h[l] <= 0 || w[l] <= 0) return 0;
+        if (!(h[l] == H && w[l] == W)) {
+            total += ((size_t)H * w[l] * C[l] * sizeof(float) + 255) / 256 * 256;
+            total += ((size_t)h[l] * (2 + ytable_len(h[l], H)) * sizeof(int32_t) + 255) / 256 * 256;
+        }
+    }
+    return total > 256 ? total : 256;
+}
+
 extern "C" int wesup_hypercolumn_bwd(const void *grad_out, int grad_dtype, int layout, const int *C, const int *h,
-                                     const int *w, int n_levels, int H, int W, void *const *grad_side, void *stream_) {
+                                     const int *w, int n_levels, int H, int W, void *const *grad_side, void *ws,
+                                     void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WESUP_REQUIRE(grad_out && grad_side, WESUP_E_ARG, "wesup_hypercolumn_bwd: null pointer");
     WESUP_REQUIRE(grad_dtype == WESUP_F32 || grad_dtype == WESUP_BF16, WESUP_E_ARG, "wesup_hypercolumn_bwd: bad dtype %d", grad_dtype);
@@ -633,6 +807,7 @@ extern "C" int wesup_hypercolumn_bwd(const void *grad_out, int grad_dtype, int l
     int rc = fill_levels(L, "wesup_hypercolumn_bwd", C, h, w, n_levels, H, W, layout);
     if (rc) return rc;
     long biggest = 0;
+    bool walk = layout == WESUP_HWC && ws != nullptr && aligned16(ws) && H <= 65535;
     for (int l = 0; l < n_levels; ++l) {
         WESUP_REQUIRE(grad_side[l] != nullptr, WESUP_E_ARG, "wesup_hypercolumn_bwd: grad_side[%d] is null", l);
         WESUP_REQUIRE(layout == WESUP_CHW || aligned16(grad_side[l]), WESUP_E_ALIGN, "wesup_hypercolumn_bwd: grad_side[%d] not 16-byte aligned", l);
@@ -641,12 +816,39 @@ extern "C" int wesup_hypercolumn_bwd(const void *grad_out, int grad_dtype, int l
         long n = (long)h[l] * w[l] * (layout == WESUP_HWC ? C[l] / 4 : C[l]);
         biggest = biggest > n ? biggest : n;
     }
-    dim3 grid(cdiv(biggest, 256), n_levels);
     if (layout == WESUP_HWC) {
         WESUP_REQUIRE(aligned16(grad_out), WESUP_E_ALIGN, "wesup_hypercolumn_bwd: grad_out not 16-byte aligned");
+        if (walk) {
+            char *p = static_cast<char *>(ws);
+            for (int l = 0; l < n_levels; ++l) {
+                L.src[l] = reinterpret_cast<const float *>(p);
+                if (!(h[l] == H && w[l] == W)) p += ((size_t)H * w[l] * C[l] * sizeof(float) + 255) / 256 * 256;
+            }
+            int32_t *tab = reinterpret_cast<int32_t *>(p);
+            size_t toff = 0;
+            int hmax = 1;
+            for (int l = 0; l < n_levels; ++l) {
+                L.ncol[l] = ytable_len(h[l], H);
+                L.soff[l] = (int)(toff / sizeof(int32_t));
+                if (!(h[l] == H && w[l] == W)) toff += ((size_t)h[l] * (2 + L.ncol[l]) * sizeof(int32_t) + 255) / 256 * 256;
+                hmax = hmax > h[l] ? hmax : h[l];
+            }
+            hyper_bwd_ytable_kernel<<<dim3(cdiv(hmax, 128), n_levels), 128, 0, stream>>>(L, tab);
+            const int groups = L.Ctot / 4;
+            const int slices = (groups + 131) / 132;                 // 132 groups (5 warps) per block
+            const int gpb = (groups + slices - 1) / slices;
+            dim3 grid1(H, slices);
+            if (grad_dtype == WESUP_F32) hyper_bwd_rows_kernel<float><<<grid1, 160, 0, stream>>>(L, (const float *)grad_out, gpb);
+            else hyper_bwd_rows_kernel<__nv_bfloat16><<<grid1, 160, 0, stream>>>(L, (const __nv_bfloat16 *)grad_out, gpb);
+            hyper_bwd_cols_kernel<<<dim3(cdiv(biggest, 256), n_levels), 256, 0, stream>>>(L, tab);
+            WESUP_CHECK_LAUNCH("wesup_hypercolumn_bwd", 3);
+            return 0;
+        }
+        dim3 grid(cdiv(biggest, 256), n_levels);
         if (grad_dtype == WESUP_F32) hyper_bwd_hwc_kernel<float><<<grid, 256, 0, stream>>>(L, (const float *)grad_out);
         else hyper_bwd_hwc_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(L, (const __nv_bfloat16 *)grad_out);
     } else {
+        dim3 grid(cdiv(biggest, 256), n_levels);
         if (grad_dtype == WESUP_F32) hyper_bwd_chw_kernel<float><<<grid, 256, 0, stream>>>(L, (const float *)grad_out);
         else hyper_bwd_chw_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(L, (const __nv_bfloat16 *)grad_out);
     }

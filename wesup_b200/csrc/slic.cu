@@ -173,11 +173,13 @@ struct Cand {
     int k, y0, y1, x0, x1;
 };
 
-__global__ void __launch_bounds__(256) slic_sweep_kernel(SlicWs s, int H, int W, long K, int step, double spatial_weight) {
+__global__ void __launch_bounds__(256, 6) slic_sweep_kernel(SlicWs s, int H, int W, long K, int step, double spatial_weight) {
     __shared__ Cand cand[MAX_CAND];
-    __shared__ double acc_c[MAX_CAND][3];
-    __shared__ unsigned int acc_n[MAX_CAND][3];
-    __shared__ int n_cand_s, is_last;
+    __shared__ double px_lab[3][256];
+    __shared__ short px_slot[256];
+    __shared__ unsigned used_bits[MAX_CAND / 32];
+    __shared__ short used_list[MAX_CAND];
+    __shared__ int n_cand_s, n_used_s, is_last;
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * AT, ty0 = blockIdx.y * AT;
     const int x = tx0 + (tid & (AT - 1)), y = ty0 + (tid >> 4);
@@ -186,11 +188,8 @@ __global__ void __launch_bounds__(256) slic_sweep_kernel(SlicWs s, int H, int W,
     const long p = (long)y * W + x;
     double pl = 0, pa = 0, pb = 0;
     if (live) { pl = s.lab[p]; pa = s.lab[HW + p]; pb = s.lab[2 * HW + p]; }
-    if (tid == 0) n_cand_s = 0;
-    for (int i = tid; i < MAX_CAND; i += 256) {
-        acc_c[i][0] = 0.0; acc_c[i][1] = 0.0; acc_c[i][2] = 0.0;
-        acc_n[i][0] = 0u; acc_n[i][1] = 0u; acc_n[i][2] = 0u;
-    }
+    if (tid == 0) { n_cand_s = 0; n_used_s = 0; }
+    if (tid < MAX_CAND / 32) used_bits[tid] = 0u;
     __syncthreads();
     // ---- gather the centres whose 2S window intersects this tile -------------
     const double two_s = (double)(2 * step);
@@ -271,35 +270,66 @@ __global__ void __launch_bounds__(256) slic_sweep_kernel(SlicWs s, int H, int W,
         }
     }
     // ---- accumulate the new cluster sums ---------------------------------------
+    // Per-tile pre-aggregation without shared-memory fp64 atomics (a CAS loop under
+    // ~40-way contention): pixels publish (slot, L, a, b); thread t then owns candidate
+    // slot t>>2 and a quarter t&3 of the tile, sums its matches in pixel order, the four
+    // quarters meet in a fixed-order shuffle tree, and one thread per touched cluster
+    // issues the global atomics (~9 clusters per tile instead of 256 pixels x 6).
+    int k_final = best_k;
     if (live) {
-        int k = best_k;
-        if (k >= 0) s.nearest[p] = k; else { k = s.nearest[p]; best_slot = -1; }   // uncovered pixel keeps its previous cluster
-        if (best_slot >= 0) {
-            atomicAdd(&acc_n[best_slot][0], 1u);
-            atomicAdd(&acc_n[best_slot][1], (unsigned)y);
-            atomicAdd(&acc_n[best_slot][2], (unsigned)x);
-            atomicAdd(&acc_c[best_slot][0], pl);
-            atomicAdd(&acc_c[best_slot][1], pa);
-            atomicAdd(&acc_c[best_slot][2], pb);
-        } else {
-            atomicAdd(&s.acc_n[3 * k], 1ull);
-            atomicAdd(&s.acc_n[3 * k + 1], (u64)y);
-            atomicAdd(&s.acc_n[3 * k + 2], (u64)x);
-            atomicAdd(&s.acc_c[3 * k], pl);
-            atomicAdd(&s.acc_c[3 * k + 1], pa);
-            atomicAdd(&s.acc_c[3 * k + 2], pb);
+        if (k_final >= 0) s.nearest[p] = k_final; else { k_final = s.nearest[p]; best_slot = -1; }   // uncovered pixel keeps its previous cluster
+        if (best_slot < 0) {                              // rare: not in the shared list -> straight to global
+            atomicAdd(&s.acc_n[3 * k_final], 1ull);
+            atomicAdd(&s.acc_n[3 * k_final + 1], (u64)y);
+            atomicAdd(&s.acc_n[3 * k_final + 2], (u64)x);
+            atomicAdd(&s.acc_c[3 * k_final], pl);
+            atomicAdd(&s.acc_c[3 * k_final + 1], pa);
+            atomicAdd(&s.acc_c[3 * k_final + 2], pb);
         }
     }
+    px_slot[tid] = (live && best_slot >= 0) ? (short)best_slot : (short)-1;
+    px_lab[0][tid] = pl; px_lab[1][tid] = pa; px_lab[2][tid] = pb;
+    if (live && best_slot >= 0) atomicOr(&used_bits[best_slot >> 5], 1u << (best_slot & 31));
     __syncthreads();
-    for (int i = tid; i < n; i += 256) {
-        if (acc_n[i][0] != 0u) {
-            const int k = cand[i].k;
-            atomicAdd(&s.acc_n[3 * k], (u64)acc_n[i][0]);
-            atomicAdd(&s.acc_n[3 * k + 1], (u64)acc_n[i][1]);
-            atomicAdd(&s.acc_n[3 * k + 2], (u64)acc_n[i][2]);
-            atomicAdd(&s.acc_c[3 * k], acc_c[i][0]);
-            atomicAdd(&s.acc_c[3 * k + 1], acc_c[i][1]);
-            atomicAdd(&s.acc_c[3 * k + 2], acc_c[i][2]);
+    if (tid < n && ((used_bits[tid >> 5] >> (tid & 31)) & 1u)) {     // dense list of the slots that own pixels (ascending)
+        int pos = __popc(used_bits[tid >> 5] & ((1u << (tid & 31)) - 1u));
+        for (int wd = 0; wd < (tid >> 5); ++wd) pos += __popc(used_bits[wd]);
+        used_list[pos] = (short)tid;
+        atomicAdd(&n_used_s, 1);
+    }
+    __syncthreads();
+    const int n_used = n_used_s;
+    for (int base = 0; base < n_used; base += 64) {
+        const int ui = base + (tid >> 2), q = tid & 3;
+        const int slot = ui < n_used ? (int)used_list[ui] : n;
+        unsigned cnt = 0, sy = 0, sx = 0;
+        double sl = 0.0, sa = 0.0, sb = 0.0;
+        if (slot < n) {
+            for (int i = q * 64; i < q * 64 + 64; ++i) {
+                if (px_slot[i] == slot) {
+                    ++cnt; sy += (unsigned)(ty0 + (i >> 4)); sx += (unsigned)(tx0 + (i & (AT - 1)));
+                    sl += px_lab[0][i]; sa += px_lab[1][i]; sb += px_lab[2][i];
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            sy += __shfl_xor_sync(0xffffffffu, sy, o);
+            sx += __shfl_xor_sync(0xffffffffu, sx, o);
+            // fixed pairing (q^1 then q^2): every lane of the quad ends with the same bits
+            const double tl = __shfl_xor_sync(0xffffffffu, sl, o), ta = __shfl_xor_sync(0xffffffffu, sa, o),
+                         tb = __shfl_xor_sync(0xffffffffu, sb, o);
+            sl = (q & o) ? tl + sl : sl + tl; sa = (q & o) ? ta + sa : sa + ta; sb = (q & o) ? tb + sb : sb + tb;
+        }
+        if (q == 0 && slot < n && cnt != 0u) {
+            const int k = cand[slot].k;
+            atomicAdd(&s.acc_n[3 * k], (u64)cnt);
+            atomicAdd(&s.acc_n[3 * k + 1], (u64)sy);
+            atomicAdd(&s.acc_n[3 * k + 2], (u64)sx);
+            atomicAdd(&s.acc_c[3 * k], sl);
+            atomicAdd(&s.acc_c[3 * k + 1], sa);
+            atomicAdd(&s.acc_c[3 * k + 2], sb);
         }
     }
     // ---- the last block to finish updates the centres and re-bins them ---------

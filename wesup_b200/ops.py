@@ -228,9 +228,11 @@ class _Hypercolumn(torch.autograd.Function):
             mem = [torch.empty((1, hh, ww, cc), dtype=torch.float32, device=dev) for cc, hh, ww in zip(C, h, w)]
         else:
             mem = [torch.empty((1, cc, hh, ww), dtype=torch.float32, device=dev) for cc, hh, ww in zip(C, h, w)]
-        check(lib.wesup_hypercolumn_bwd(grad_out.data_ptr(), _DTYPES[grad_out.dtype], layout, _lib.int_array(C),
-                                        _lib.int_array(h), _lib.int_array(w), len(C), H, W,
-                                        _lib.ptr_array([m.data_ptr() for m in mem]), _stream()), "wesup_hypercolumn_bwd")
+        ca, ha, wa = _lib.int_array(C), _lib.int_array(h), _lib.int_array(w)
+        ws = _ws(lib.wesup_hypercolumn_bwd_workspace_bytes(ca, ha, wa, len(C), H, W), dev) if layout == HWC else None
+        check(lib.wesup_hypercolumn_bwd(grad_out.data_ptr(), _DTYPES[grad_out.dtype], layout, ca, ha, wa, len(C), H, W,
+                                        _lib.ptr_array([m.data_ptr() for m in mem]),
+                                        ws.data_ptr() if ws is not None else None, _stream()), "wesup_hypercolumn_bwd")
         grads = [m.permute(0, 3, 1, 2) if layout == HWC else m for m in mem]
         return (None, None, None, *grads)
 
