@@ -102,6 +102,14 @@ int wesup_sp_pool_fwd(const void *feat, int dtype, int layout, const int32_t *se
 int wesup_sp_pool_bwd(const float *grad_pooled, const int32_t *row_labels, const int32_t *counts,
                       int HW, int C, int N, void *grad_feat, int dtype, int layout, void *stream);
 
+/* fused (b) o (a): per-superpixel means of the hypercolumn computed directly from
+ * the side outputs (pixel-major, WESUP_HWC) -- equals wesup_hypercolumn_fwd followed
+ * by wesup_sp_pool_fwd (models/wesup.py:254-261 then :284-285) without writing the
+ * (H*W, sum C) tensor.  `side`, `C`, `h`, `w` are HOST arrays.  pooled: (N, sum C) fp32. */
+int wesup_hypercolumn_pool_fwd(const void *const *side, const int *C, const int *h, const int *w,
+                               int n_levels, int H, int W, const int32_t *seg_offsets,
+                               const int32_t *seg_pixels, int N, float *pooled, void *stream);
+
 /* fused adjoint of (b) o (a): what autograd derives for the mm at
  * models/wesup.py:284-285 followed by the cat + interpolate chain at :254-261,
  * evaluated from the pooled gradient (N, sum C) directly -- the (H*W, sum C)

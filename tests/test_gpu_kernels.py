@@ -268,6 +268,26 @@ def test_fused_pool_hypercolumn_backward_vs_autograd_of_dense_reference(h, w, n,
             assert rel_err(x.grad, y.grad) < 1e-6
 
 
+@pytest.mark.parametrize("h,w,n", [(48, 40, 30), (37, 51, 7), (131, 97, 60), (464, 464, 1076)])
+def test_fused_forward_equals_hypercolumn_then_pool(h, w, n):
+    """Pooling straight from the side outputs == kernel (a) then kernel (b) (same arithmetic, same order)."""
+    gen = torch.Generator().manual_seed(h + w + n)
+    seg = torch.from_numpy(synth.perturbed_grid_segments(h, w, max(2, int((h * w / n) ** 0.5)), seed=n)).long()
+    sp = SuperpixelMaps.from_labels(seg.to(DEV))
+    xs = [s.to(DEV).requires_grad_(True) for s in make_sides(h, w, seed=n)]
+    ys = [x.detach().clone().requires_grad_(True) for x in xs]
+    pooled_a, feats = ops.hypercolumn_pool(xs, (h, w), sp)
+    pooled_b, none = ops.hypercolumn_pool(ys, (h, w), sp, materialize=False)
+    assert none is None and feats is not None
+    assert rel_err(pooled_b, pooled_a) < 1e-6
+    np.testing.assert_allclose(pooled_b.cpu().numpy(), pooled_a.detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
+    g = torch.randn(pooled_a.shape, generator=gen).to(DEV)
+    pooled_a.backward(g)
+    pooled_b.backward(g)
+    for x, y in zip(xs, ys):
+        assert torch.equal(x.grad, y.grad)                                   # same fused backward either way
+
+
 def test_fused_backward_full_size_adjoint_identity():
     """<pool(hyper(x)), g> == <x, fused_bwd(g)> at 464^2 with a SLIC-like grid of superpixels."""
     h = w = 464

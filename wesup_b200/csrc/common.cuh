@@ -134,4 +134,16 @@ static inline float bilinear_scale(int in_size, int out_size) {
     return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.0f;
 }
 
+// Geometry of the side outputs (one entry per VGG16 conv level), passed by value to the
+// hypercolumn kernels.
+struct Levels {
+    const float *src[WESUP_MAX_LEVELS];   // fwd: side outputs; bwd: unused
+    float *dst[WESUP_MAX_LEVELS];         // bwd: side gradients
+    int C[WESUP_MAX_LEVELS], h[WESUP_MAX_LEVELS], w[WESUP_MAX_LEVELS], coff[WESUP_MAX_LEVELS];
+    float sy[WESUP_MAX_LEVELS], sx[WESUP_MAX_LEVELS];
+    int ncol[WESUP_MAX_LEVELS];           // bulk-staged kernels: staged source columns per row (upper bound per segment)
+    int soff[WESUP_MAX_LEVELS];           // bulk-staged kernels: float offset of the level's staging area
+    int n, H, W, Ctot;
+};
+
 }  // namespace wesup

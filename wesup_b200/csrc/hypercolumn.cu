@@ -17,15 +17,6 @@
 
 namespace wesup {
 
-struct Levels {
-    const float *src[WESUP_MAX_LEVELS];   // fwd: side outputs; bwd: unused
-    float *dst[WESUP_MAX_LEVELS];         // bwd: side gradients
-    int C[WESUP_MAX_LEVELS], h[WESUP_MAX_LEVELS], w[WESUP_MAX_LEVELS], coff[WESUP_MAX_LEVELS];
-    float sy[WESUP_MAX_LEVELS], sx[WESUP_MAX_LEVELS];
-    int ncol[WESUP_MAX_LEVELS];           // bulk-staged kernels: staged source columns per row (upper bound per segment)
-    int soff[WESUP_MAX_LEVELS];           // bulk-staged kernels: float offset of the level's staging area
-    int n, H, W, Ctot;
-};
 
 constexpr int TILE_W = 16, TILE_H = 4, TILE_PX = TILE_W * TILE_H;
 

@@ -310,15 +310,22 @@ class _HypercolumnPool(torch.autograd.Function):
         mem = [_as_hwc(s) for s in sides]
         ctot = sum(C)
         dev = sides[0].device
-        feats = torch.empty((H * W, ctot), dtype=dtype, device=dev)
-        check(lib.wesup_hypercolumn_fwd(_lib.ptr_array([m.data_ptr() for m in mem]), _lib.int_array(C), _lib.int_array(h),
-                                        _lib.int_array(w), len(sides), H, W, feats.data_ptr(), _DTYPES[dtype], HWC,
-                                        _stream()), "wesup_hypercolumn_fwd")
         pooled = torch.empty((sp.n, ctot), dtype=torch.float32, device=dev)
-        check(lib.wesup_sp_pool_fwd(feats.data_ptr(), _DTYPES[dtype], HWC, sp.seg_offsets.data_ptr(),
-                                    sp.seg_pixels.data_ptr(), H * W, ctot, sp.n, pooled.data_ptr(), _stream()),
-              "wesup_sp_pool_fwd")
+        ptrs, ca, ha, wa = _lib.ptr_array([m.data_ptr() for m in mem]), _lib.int_array(C), _lib.int_array(h), _lib.int_array(w)
         ctx.sp, ctx.geom = sp, (C, h, w, H, W)
+        if dtype is None:
+            # fully fused: superpixel means straight from the side outputs, no (H*W, C) tensor
+            check(lib.wesup_hypercolumn_pool_fwd(ptrs, ca, ha, wa, len(sides), H, W, sp.seg_offsets.data_ptr(),
+                                                 sp.seg_pixels.data_ptr(), sp.n, pooled.data_ptr(), _stream()),
+                  "wesup_hypercolumn_pool_fwd")
+            feats = torch.empty(0, dtype=torch.float32, device=dev)
+        else:
+            feats = torch.empty((H * W, ctot), dtype=dtype, device=dev)
+            check(lib.wesup_hypercolumn_fwd(ptrs, ca, ha, wa, len(sides), H, W, feats.data_ptr(), _DTYPES[dtype], HWC,
+                                            _stream()), "wesup_hypercolumn_fwd")
+            check(lib.wesup_sp_pool_fwd(feats.data_ptr(), _DTYPES[dtype], HWC, sp.seg_offsets.data_ptr(),
+                                        sp.seg_pixels.data_ptr(), H * W, ctot, sp.n, pooled.data_ptr(), _stream()),
+                  "wesup_sp_pool_fwd")
         ctx.mark_non_differentiable(feats)
         return pooled, feats
 
@@ -339,10 +346,15 @@ class _HypercolumnPool(torch.autograd.Function):
         return (None, None, None, *[m.permute(0, 3, 1, 2) for m in mem])
 
 
-def hypercolumn_pool(sides: Sequence[torch.Tensor], size: Tuple[int, int], sp: SuperpixelMaps, dtype=torch.float32):
+def hypercolumn_pool(sides: Sequence[torch.Tensor], size: Tuple[int, int], sp: SuperpixelMaps, dtype=torch.float32,
+                     materialize: bool = True):
     """Hypercolumn (a) + superpixel mean pooling (b) with the fused backward.
-    Returns (pooled (N,C) fp32, feats (H*W,C) `dtype`, non-differentiable)."""
-    return _HypercolumnPool.apply(sp, (int(size[0]), int(size[1])), dtype, *sides)
+    Returns (pooled (N,C) fp32, feats).  materialize=True (default): `feats` is the
+    (H*W,C) `dtype` hypercolumn written by kernel (a) (non-differentiable output).
+    materialize=False: one fused forward kernel pools straight from the side outputs,
+    `feats` is None and nothing of size H*W*C is ever allocated."""
+    pooled, feats = _HypercolumnPool.apply(sp, (int(size[0]), int(size[1])), dtype if materialize else None, *sides)
+    return pooled, (feats if materialize else None)
 
 
 def paint(sp: SuperpixelMaps, sp_pred: torch.Tensor, cls: int = 1) -> torch.Tensor:
