@@ -159,7 +159,8 @@ def test_pool_large_properties():
     y.backward(gp)
     lhs = (y.detach().double() * gp.double()).sum()
     rhs = (x.detach().double() * x.grad.double()).sum()
-    assert abs(float(lhs - rhs)) < 1e-6 * abs(float(lhs)) + 1e-6
+    scale = float((y.detach().double() * gp.double()).abs().sum())      # fp32 rounding scales with the terms, not their sum
+    assert abs(float(lhs - rhs)) < 1e-6 * scale + 1e-6
 
 
 def test_paint_matches_reference_loop():
@@ -280,7 +281,7 @@ def test_fused_forward_equals_hypercolumn_then_pool(h, w, n):
     pooled_b, none = ops.hypercolumn_pool(ys, (h, w), sp, materialize=False)
     assert none is None and feats is not None
     assert rel_err(pooled_b, pooled_a) < 1e-6
-    np.testing.assert_allclose(pooled_b.cpu().numpy(), pooled_a.detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(pooled_b.detach().cpu().numpy(), pooled_a.detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
     g = torch.randn(pooled_a.shape, generator=gen).to(DEV)
     pooled_a.backward(g)
     pooled_b.backward(g)
