@@ -216,17 +216,39 @@ def kernel_rooflines(dev, peak_gbs):
             ca, ha, wa = ia(Cs), ia(hs), ia(ws_)
             sptrs = ops._lib.ptr_array([s.permute(0, 2, 3, 1).contiguous().data_ptr() for s in sides])
             pooled_f = torch.empty(n_sp, C_HYPER, device=dev)
-            ms = time_kernel(lambda: lib.wesup_hypercolumn_pool_fwd(sptrs, ca, ha, wa, 13, H, W, sp.seg_offsets.data_ptr(),
-                                                                    sp.seg_pixels.data_ptr(), n_sp, pooled_f.data_ptr(), st), 10, flush)
+            ms = time_kernel(lambda: lib.wesup_hypercolumn_pool_fwd_walk(sptrs, ca, ha, wa, 13, H, W, sp.seg_offsets.data_ptr(),
+                                                                         sp.seg_pixels.data_ptr(), n_sp, pooled_f.data_ptr(), st), 10, flush)
             b = side_bytes + hw * 4 + n_sp * C_HYPER * 4 + n_sp * 4
-            out["hypercolumn_pool_fwd_fused"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6,
-                                                 "replaces_ms": out["hypercolumn_fwd_f32"]["ms"] + out["sp_pool_fwd_f32"]["ms"]}
+            out["hypercolumn_pool_fwd_walk"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
             fws = torch.empty(lib.wesup_sp_pool_hypercolumn_bwd_workspace_bytes(ca, ha, wa, 13, H, W, n_sp), dtype=torch.uint8, device=dev)
-            ms = time_kernel(lambda: lib.wesup_sp_pool_hypercolumn_bwd(gp.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
-                                                                       ca, ha, wa, 13, H, W, n_sp, ptrs, fws.data_ptr(), st), 10, flush)
+            ms = time_kernel(lambda: lib.wesup_sp_pool_hypercolumn_bwd_walk(gp.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
+                                                                            ca, ha, wa, 13, H, W, n_sp, ptrs, fws.data_ptr(), st), 10, flush)
             b = side_bytes + hw * 4 + 2 * n_sp * C_HYPER * 4 + n_sp * 4
-            out["pool_hypercolumn_bwd_fused"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6,
-                                                 "replaces_ms": out["sp_pool_bwd_f32"]["ms"] + out["hypercolumn_bwd_f32"]["ms"]}
+            out["pool_hypercolumn_bwd_walk"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
+            # footprint kernels: on the 13 side outputs (2112 channels) and on the 13 backbone outputs (4224, "pool first")
+            for tag, mult in (("side2112", 1), ("backbone4224", 2)):
+                lv = sides if mult == 1 else [torch.randn(1, 2 * c, H >> s_, W >> s_, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+                                              for c, s_ in zip(VGG_C, VGG_SHIFT)]
+                lv_mem = [t.permute(0, 2, 3, 1).contiguous() for t in lv]
+                lv_bytes = sum(t.numel() * 4 for t in lv_mem)
+                ctot = mult * C_HYPER
+                lca = ia([t.size(3) for t in lv_mem])
+                lptrs = ops._lib.ptr_array([t.data_ptr() for t in lv_mem])
+                pooled_l = torch.empty(n_sp, ctot, device=dev)
+                ms = time_kernel(lambda: lib.wesup_levels_pool_fwd(lptrs, lca, ha, wa, 13, H, W, sp.seg_offsets.data_ptr(),
+                                                                   sp.seg_pixels.data_ptr(), n_sp, pooled_l.data_ptr(), st), 10, flush)
+                b = lv_bytes + hw * 4 + n_sp * ctot * 4 + n_sp * 4
+                out[f"levels_pool_fwd_{tag}"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
+                gl = [torch.empty_like(t) for t in lv_mem]
+                gptrs = ops._lib.ptr_array([t.data_ptr() for t in gl])
+                gpl = torch.randn(n_sp, ctot, device=dev)
+                ms = time_kernel(lambda: lib.wesup_levels_pool_bwd(gpl.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
+                                                                   lca, ha, wa, 13, H, W, n_sp, gptrs, st), 10, flush)
+                b = lv_bytes + hw * 4 + n_sp * ctot * 4 + n_sp * 4
+                out[f"levels_pool_bwd_{tag}"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
+                del lv_mem, gl, gpl, pooled_l
+            out["levels_pool_fwd_side2112"]["replaces_ms"] = out["hypercolumn_fwd_f32"]["ms"] + out["sp_pool_fwd_f32"]["ms"]
+            out["levels_pool_bwd_side2112"]["replaces_ms"] = out["sp_pool_bwd_f32"]["ms"] + out["hypercolumn_bwd_f32"]["ms"]
         del feats, gf
     ms = time_kernel(lambda: ops.slic(x, int(hw / 200), 40), 10, flush)
     b = hw * 360
@@ -273,7 +295,8 @@ def run_own(args):
     dev = torch.device("cuda", local)
     torch.manual_seed(0)
     lib = _lib.load()
-    trainer = initialize_trainer("wesup", device=dev, pretrained=False, materialize_hypercolumn=not args.no_materialize)
+    trainer = initialize_trainer("wesup", device=dev, pretrained=False, materialize_hypercolumn=args.materialize,
+                                 pool_first=not args.no_pool_first)
     trainer.optimizer, _ = trainer.get_default_optimizer()
     trainer.metric_funcs = [accuracy, dice]
     if world > 1:
@@ -293,6 +316,8 @@ def run_own(args):
             if not args.no_prefetch:
                 trainer.prefetch(*samples[(k + 1) % pool])
             trainer.train_one_iteration("train", *samples[k % pool])
+        if i == last_step[0]:
+            trainer.flush_metrics()          # the last iteration's loss is read inside the timed region too
 
     def step_resident(i):
         run_step(resident, i)
@@ -305,7 +330,10 @@ def run_own(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    last_step = [-1]
+
     def timed(step_fn, steps):
+        last_step[0] = steps - 1
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.wesup_kernel_launches()
@@ -339,15 +367,27 @@ def run_own(args):
     kernels = kernel_rooflines(dev, peak) if not args.skip_kernels else {}
     roofline = None
     if kernels:
-        # the largest HBM-bound launch of the step: the fused upsample+concat write of the hypercolumn
-        k = kernels["hypercolumn_fwd_f32"]
-        name = "void hyper_fwd_bulk_kernel<float, 4>(Levels, T1 *, int)"
+        # the dominant superpixel-stage launch of the step that was timed
+        per_image_ms = ms_total / args.steps / ips
+        if args.materialize:
+            key, name, label = "hypercolumn_fwd_f32", "void hyper_fwd_bulk_kernel<float, 4>(Levels, T1 *, int)", \
+                "hyper_fwd_bulk_kernel<float,4> (wesup_hypercolumn_fwd)"
+        else:
+            tag = "side2112" if args.no_pool_first else "backbone4224"
+            key = max((f"levels_pool_fwd_{tag}", f"levels_pool_bwd_{tag}"), key=lambda k_: kernels[k_]["ms"])
+            if "fwd" in key:
+                name, label = "levels_pool_fwd_kernel(Levels, Groups, const int *, const int *, float *)", \
+                    "levels_pool_fwd_kernel (wesup_levels_pool_fwd)"
+            else:
+                name, label = "levels_pool_bwd_kernel", "levels_pool_bwd_kernel<V> x 5 resolution groups (wesup_levels_pool_bwd)"
+        k = kernels[key]
         traffic = None
         tfile = ROOT / "profiles" / "roofline_traffic.json"
         if tfile.exists():
-            traffic = json.loads(tfile.read_text()).get(name, {}).get("traffic_bytes")
-        per_image_ms = ms_total / args.steps / ips
-        roofline = {"kernel": "hyper_fwd_bulk_kernel<float,4> (wesup_hypercolumn_fwd)", "bound": "hbm", "achieved": k["gbs"],
+            tj = json.loads(tfile.read_text())
+            hits = [v["traffic_bytes"] for n_, v in tj.items() if isinstance(v, dict) and name.split("(")[0] in n_]
+            traffic = sum(hits) if hits else None
+        roofline = {"kernel": label, "bound": "hbm", "achieved": k["gbs"],
                     "peak": peak, "peak_source": peak_src + ": a read+write copy; write-only streams measure 7.4 TB/s on this pool",
                     "unit": "GB/s", "frac": k["gbs"] / peak, "traffic": traffic,
                     "algorithmic_bytes_per_launch": k["bytes"], "ms_per_launch": k["ms"],
@@ -367,7 +407,9 @@ def run_own(args):
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "WESUP train step 464x464, batch-1 SGD, 1e-4 point labels, random-init VGG16",
-                       "images_per_step": ips, "images_per_step_all_ranks": ips * world, "hypercolumn": "not materialised (fused forward)" if args.no_materialize else "f32 pixel-major (H*W,2112)",
+                       "images_per_step": ips, "images_per_step_all_ranks": ips * world, "hypercolumn": "f32 pixel-major (H*W,2112)" if args.materialize else
+                       ("not materialised: superpixel means from the 13 side outputs" if args.no_pool_first else
+                        "not materialised: superpixel means from the 13 backbone levels (4224 ch), side convs on the N pooled rows"),
                        "parallelism": f"dp{world}", "l2": "working set 1.8 GB/image (hypercolumn) >> 126 MB L2; "
                        "kernel microbenches flush L2 with a 256 MB write before every launch",
                        "cudnn_tf32": bool(torch.backends.cudnn.allow_tf32)},
@@ -381,14 +423,19 @@ def run_own(args):
 
 
 def main():
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--images-per-step", type=int, default=4)
-    ap.add_argument("--no-materialize", action="store_true",
-                    help="opt-in fully fused forward: pool straight from the side outputs, never write the hypercolumn")
+    ap.add_argument("--materialize", action="store_true",
+                    help="classic path: kernel (a) writes the (H*W,2112) hypercolumn, kernel (b) pools it (default: fused, "
+                         "superpixel means straight from the backbone levels, side convs on the pooled rows)")
+    ap.add_argument("--no-pool-first", action="store_true",
+                    help="fused path over the 13 side outputs (side convs on H*W pixels) instead of pool-first")
     ap.add_argument("--no-prefetch", action="store_true", help="preprocess inline instead of one image ahead on a side stream")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-kernels", action="store_true", help="omit the per-kernel roofline microbench")

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define WESUP_ABI_VERSION 3
+#define WESUP_ABI_VERSION 4
 #define WESUP_MAX_LEVELS 16
 
 /* element type of the hypercolumn tensor */
@@ -102,26 +102,49 @@ int wesup_sp_pool_fwd(const void *feat, int dtype, int layout, const int32_t *se
 int wesup_sp_pool_bwd(const float *grad_pooled, const int32_t *row_labels, const int32_t *counts,
                       int HW, int C, int N, void *grad_feat, int dtype, int layout, void *stream);
 
-/* fused (b) o (a): per-superpixel means of the hypercolumn computed directly from
- * the side outputs (pixel-major, WESUP_HWC) -- equals wesup_hypercolumn_fwd followed
- * by wesup_sp_pool_fwd (models/wesup.py:254-261 then :284-285) without writing the
- * (H*W, sum C) tensor.  `side`, `C`, `h`, `w` are HOST arrays.  pooled: (N, sum C) fp32. */
+/* ---- fused (b) o (a): superpixel means straight from the feature levels -------
+ * pooled = wesup_sp_pool_fwd(wesup_hypercolumn_fwd(level)) (models/wesup.py:254-261
+ * then :284-285) WITHOUT the (H*W, sum C) tensor, in the footprint formulation: the
+ * bilinear tap weights of a superpixel's pixels are aggregated once per low-resolution
+ * cell (scalar work shared by all channels and all levels of that resolution), then
+ *   pooled[k, coff_l + c] = 1/|S_k| * sum_cells G_k(cell) * level_l[cell, c].
+ * level[l]: fp32 pixel-major (h[l], w[l], C[l]); `level`, `C`, `h`, `w` are HOST arrays;
+ * pooled: (N, sum C) fp32.  Callers: the 13 side outputs (sum C = 2112), or the 13
+ * backbone conv outputs ("pool first", sum C = 4224) followed by the 1x1 side
+ * convolutions on N rows -- mean and 1x1 conv commute.  C[l] % 4 == 0, C[l] <= 1536. */
+int wesup_levels_pool_fwd(const void *const *level, const int *C, const int *h, const int *w,
+                          int n_levels, int H, int W, const int32_t *seg_offsets,
+                          const int32_t *seg_pixels, int N, float *pooled, void *stream);
+/* adjoint of the above (what autograd derives for the mm at models/wesup.py:284-285
+ * followed by the cat + interpolate chain at :254-261), evaluated from the pooled
+ * gradient (N, sum C): grad_level[l] (fp32 (h[l], w[l], C[l]), fully overwritten).
+ * One warp per low-resolution cell: walks the cell's footprint of the label map once,
+ * then gathers grad_pooled rows of the distinct superpixels it meets.  Deterministic. */
+int wesup_levels_pool_bwd(const float *grad_pooled, const int32_t *row_labels, const int32_t *counts,
+                          const int *C, const int *h, const int *w, int n_levels, int H, int W,
+                          int N, void *const *grad_level, void *stream);
+
+/* Historical names of the fused path (same signatures as ABI 3): they now run the two
+ * footprint kernels above; `ws` is unused (any pointer, the size function still answers). */
 int wesup_hypercolumn_pool_fwd(const void *const *side, const int *C, const int *h, const int *w,
                                int n_levels, int H, int W, const int32_t *seg_offsets,
                                const int32_t *seg_pixels, int N, float *pooled, void *stream);
-
-/* fused adjoint of (b) o (a): what autograd derives for the mm at
- * models/wesup.py:284-285 followed by the cat + interpolate chain at :254-261,
- * evaluated from the pooled gradient (N, sum C) directly -- the (H*W, sum C)
- * gradient of the hypercolumn is never written.  grad_side[l]: fp32
- * (h[l],w[l],C[l]) pixel-major (WESUP_HWC); C/h/w/grad_side are HOST arrays.
- * Deterministic (gather form). */
 size_t wesup_sp_pool_hypercolumn_bwd_workspace_bytes(const int *C, const int *h, const int *w,
                                                      int n_levels, int H, int W, int N);
 int wesup_sp_pool_hypercolumn_bwd(const float *grad_pooled, const int32_t *row_labels,
                                   const int32_t *counts, const int *C, const int *h, const int *w,
                                   int n_levels, int H, int W, int N, void *const *grad_side,
                                   void *ws, void *stream);
+/* The per-pixel walk formulation of the same two operators (4 taps per pixel per channel;
+ * kept as an independent cross-check of the footprint kernels and as their measured
+ * predecessor).  The bwd needs `ws` of wesup_sp_pool_hypercolumn_bwd_workspace_bytes. */
+int wesup_hypercolumn_pool_fwd_walk(const void *const *side, const int *C, const int *h, const int *w,
+                                    int n_levels, int H, int W, const int32_t *seg_offsets,
+                                    const int32_t *seg_pixels, int N, float *pooled, void *stream);
+int wesup_sp_pool_hypercolumn_bwd_walk(const float *grad_pooled, const int32_t *row_labels,
+                                       const int32_t *counts, const int *C, const int *h, const int *w,
+                                       int n_levels, int H, int W, int N, void *const *grad_side,
+                                       void *ws, void *stream);
 
 /* ---- paint: replaces argmax + per-superpixel index_put loop -----------------
  * (models/wesup.py:295-304): out[p] = sp_pred[row_labels[p], cls]. */

@@ -289,6 +289,62 @@ def test_fused_forward_equals_hypercolumn_then_pool(h, w, n):
         assert torch.equal(x.grad, y.grad)                                   # same fused backward either way
 
 
+FULL_C = [64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512]      # backbone conv outputs ("pool first")
+
+
+def _levels_call(name, *args):
+    from wesup_b200 import _lib
+    _lib.check(getattr(_lib.load(), name)(*args), name)
+
+
+@pytest.mark.parametrize("h,w,n,channels", [(48, 40, 30, VGG_C), (131, 97, 60, VGG_C), (96, 112, 50, FULL_C),
+                                            (464, 464, 1076, FULL_C), (200, 180, 3, VGG_C)])
+def test_footprint_kernels_match_the_per_pixel_walk_kernels(h, w, n, channels):
+    """wesup_levels_pool_fwd/bwd (weights aggregated per low-res cell) against the independent per-pixel
+    walk formulation of the same operators, on SLIC-like grids, on a few huge superpixels (bounding box
+    larger than the shared grid => per-pixel path inside the kernel) and with the 4224 backbone channels."""
+    from wesup_b200 import _lib
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    seg = torch.from_numpy(synth.perturbed_grid_segments(h, w, max(2, int((h * w / n) ** 0.5)), seed=n)).long()
+    sp = SuperpixelMaps.from_labels(seg.to(DEV))
+    sides = [s.to(DEV).permute(0, 2, 3, 1).contiguous() for s in make_sides(h, w, seed=n, channels=channels)]
+    C, hs, ws_ = [s.size(3) for s in sides], [s.size(1) for s in sides], [s.size(2) for s in sides]
+    ca, ha, wa = _lib.int_array(C), _lib.int_array(hs), _lib.int_array(ws_)
+    ptrs = _lib.ptr_array([s.data_ptr() for s in sides])
+    ctot = sum(C)
+    a = torch.empty(sp.n, ctot, device=DEV)
+    b = torch.empty(sp.n, ctot, device=DEV)
+    _levels_call("wesup_levels_pool_fwd", ptrs, ca, ha, wa, len(C), h, w, sp.seg_offsets.data_ptr(), sp.seg_pixels.data_ptr(),
+                 sp.n, a.data_ptr(), st)
+    _levels_call("wesup_hypercolumn_pool_fwd_walk", ptrs, ca, ha, wa, len(C), h, w, sp.seg_offsets.data_ptr(),
+                 sp.seg_pixels.data_ptr(), sp.n, b.data_ptr(), st)
+    tol = 1e-6 if h * w / sp.n < 2000 else 1e-5          # fp32 sums over 12 000-pixel superpixels in two different orders
+    assert rel_err(a, b) < tol
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-5, atol=2e-6)
+    gp = torch.randn(sp.n, ctot, device=DEV)
+    ga = [torch.full_like(s, float("nan")) for s in sides]          # every element must be overwritten
+    gb = [torch.empty_like(s) for s in sides]
+    _levels_call("wesup_levels_pool_bwd", gp.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(), ca, ha, wa, len(C), h, w,
+                 sp.n, _lib.ptr_array([t.data_ptr() for t in ga]), st)
+    wsb = torch.empty(lib.wesup_sp_pool_hypercolumn_bwd_workspace_bytes(ca, ha, wa, len(C), h, w, sp.n), dtype=torch.uint8, device=DEV)
+    _levels_call("wesup_sp_pool_hypercolumn_bwd_walk", gp.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(), ca, ha, wa,
+                 len(C), h, w, sp.n, _lib.ptr_array([t.data_ptr() for t in gb]), wsb.data_ptr(), st)
+    for x, y in zip(ga, gb):
+        assert torch.isfinite(x).all()
+        assert rel_err(x, y) < tol
+    # adjoint identity of the footprint pair itself
+    lhs = (a.double() * gp.double()).sum()
+    rhs = sum((s.double() * g.double()).sum() for s, g in zip(sides, ga))
+    scale = float((a.double() * gp.double()).abs().sum())
+    assert abs(float(lhs - rhs)) < 1e-6 * scale + 1e-6
+    # run-to-run determinism (fixed summation order, no floating-point atomics)
+    a2 = torch.empty_like(a)
+    _levels_call("wesup_levels_pool_fwd", ptrs, ca, ha, wa, len(C), h, w, sp.seg_offsets.data_ptr(), sp.seg_pixels.data_ptr(),
+                 sp.n, a2.data_ptr(), st)
+    assert torch.equal(a, a2)
+
+
 def test_fused_backward_full_size_adjoint_identity():
     """<pool(hyper(x)), g> == <x, fused_bwd(g)> at 464^2 with a SLIC-like grid of superpixels."""
     h = w = 464

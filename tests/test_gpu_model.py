@@ -33,11 +33,12 @@ def build(cls=WESUP, **kw):
     return model.to(DEV)
 
 
-@pytest.mark.parametrize("layout,fused,materialize", [("hwc", True, True), ("hwc", False, True), ("chw", False, True),
-                                                     ("hwc", True, False)])
-def test_forward_loss_backward_matches_reference(golden, layout, fused, materialize):
+@pytest.mark.parametrize("layout,fused,materialize,pool_first", [("hwc", True, True, False), ("hwc", False, True, False),
+                                                                ("chw", False, True, False), ("hwc", True, False, False),
+                                                                ("hwc", True, False, True)])
+def test_forward_loss_backward_matches_reference(golden, layout, fused, materialize, pool_first):
     g = golden("forward_loss_backward_48x40.npz")
-    model = build(hc_layout=layout, fused_backward=fused, materialize_hypercolumn=materialize)
+    model = build(hc_layout=layout, fused_backward=fused, materialize_hypercolumn=materialize, pool_first=pool_first)
     trainer = WESUPTrainer(model, device=DEV)
     x = synth.to_tensor(g["img_u8"]).unsqueeze(0).to(DEV)
     sp_maps, sp_labels = _preprocess_superpixels(torch.from_numpy(g["segments"]).to(DEV),
@@ -171,6 +172,8 @@ def test_trainer_preprocess_and_train_iteration_end_to_end():
     from wesup_b200.utils.metrics import accuracy, dice
     trainer.metric_funcs = [accuracy, dice]
     trainer.train_one_iteration("train", img, pixel_mask, point_mask)
+    assert "loss" not in trainer.tracker.history       # default metrics_lag=1: scalars are read one iteration later
+    trainer.flush_metrics()
     assert "loss" in trainer.tracker.history and "dice" in trainer.tracker.history
 
 
@@ -208,5 +211,28 @@ def test_prefetched_preprocess_is_identical_and_single_use():
     # a full iteration through the prefetch path
     trainer.optimizer, _ = trainer.get_default_optimizer()
     trainer.train_one_iteration("train", *b)
+    trainer.flush_metrics()
     assert len(trainer._prefetched) == 0
     assert np.isfinite(trainer.tracker.history["loss"][-1])
+
+
+def test_metrics_lag_zero_reads_in_the_same_iteration_and_nan_raises():
+    from wesup_b200.utils.metrics import accuracy, dice
+    trainer = initialize_trainer("wesup", device=DEV, pretrained=False, metrics_lag=0)
+    trainer.optimizer, _ = trainer.get_default_optimizer()
+    trainer.metric_funcs = [accuracy, dice]
+    b = synth.sample(96, 112, index=6, ratio=2e-3)
+    trainer.train_one_iteration("train", *b)
+    assert len(trainer.tracker.history["loss"]) == 1 and np.isfinite(trainer.tracker.history["loss"][-1])
+    with torch.no_grad():
+        trainer.model.classifier[0].weight.fill_(float("nan"))
+    with pytest.raises(ValueError, match="Loss is nan!"):
+        trainer.train_one_iteration("train", *b)
+    # lagged mode: the same error surfaces when the scalars are read
+    lagged = initialize_trainer("wesup", device=DEV, pretrained=False)
+    lagged.optimizer, _ = lagged.get_default_optimizer()
+    with torch.no_grad():
+        lagged.model.classifier[0].weight.fill_(float("nan"))
+    lagged.train_one_iteration("train", *b)
+    with pytest.raises(ValueError, match="Loss is nan!"):
+        lagged.flush_metrics()

@@ -25,12 +25,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--images", type=int, default=8)
     ap.add_argument("--no-materialize", action="store_true")
+    ap.add_argument("--no-pool-first", action="store_true")
+    ap.add_argument("--host", action="store_true", help="also print where the host time goes")
     ap.add_argument("--size", type=int, nargs=2, default=[bench.H, bench.W])
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     h, w = a.size
-    trainer = initialize_trainer("wesup", device=dev, pretrained=False, materialize_hypercolumn=not a.no_materialize)
+    trainer = initialize_trainer("wesup", device=dev, pretrained=False, materialize_hypercolumn=not a.no_materialize,
+                                 pool_first=not a.no_pool_first)
     trainer.optimizer, _ = trainer.get_default_optimizer()
     trainer.metric_funcs = [accuracy, dice]
     pool = 4
@@ -40,11 +43,13 @@ def main():
         for k in range(n):
             trainer.prefetch(*data[(k + 1) % pool])
             trainer.train_one_iteration("train", *data[k % pool])
+        trainer.flush_metrics()
 
     run(6)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     run(a.images)
+    enqueue = (time.perf_counter() - t0) / a.images * 1e3      # host time to enqueue (includes the per-image host waits)
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / a.images * 1e3
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
@@ -59,12 +64,31 @@ def main():
             total += ev.device_time
             launches += 1
     n = a.images
-    print(f"# step profile {h}x{w}, {n} images, materialize={not a.no_materialize}\n")
-    print(f"wall (unprofiled) {wall:.3f} ms/image; summed device time {total / n / 1e3:.3f} ms/image; "
+    print(f"# step profile {h}x{w}, {n} images, materialize={not a.no_materialize} pool_first={not a.no_pool_first}\n")
+    print(f"host enqueue {enqueue:.3f} ms/image; wall (unprofiled) {wall:.3f} ms/image; summed device time {total / n / 1e3:.3f} ms/image; "
           f"{launches / n:.0f} device activities/image\n")
     print("| us/image | share | n/image | kernel |\n|---:|---:|---:|---|")
     for name, (us, cnt) in sorted(per.items(), key=lambda kv: -kv[1][0])[:45]:
         print(f"| {us / n:.1f} | {100 * us / total:.1f} % | {cnt / n:.1f} | `{name[:110]}` |")
+
+
+    if a.host:
+        print("\n## host side (self CPU time per image)\n\n| us/image | calls/image | op |\n|---:|---:|---|")
+        for ev in sorted(prof.key_averages(), key=lambda e: -e.self_cpu_time_total)[:40]:
+            print(f"| {ev.self_cpu_time_total / n:.1f} | {ev.count / n:.1f} | `{ev.key[:90]}` |")
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        run(a.images)
+        torch.cuda.synchronize()
+        pr.disable()
+        print("\n## cProfile (cumulative, python frames)\n\n```")
+        import io
+        buf = io.StringIO()
+        pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(45)
+        print(buf.getvalue()[:9000])
+        print("```")
 
 
 if __name__ == "__main__":

@@ -172,24 +172,24 @@ extern "C" size_t wesup_sp_pool_hypercolumn_bwd_workspace_bytes(const int *C, co
     return P.total;
 }
 
-extern "C" int wesup_sp_pool_hypercolumn_bwd(const float *grad_pooled, const int32_t *row_labels, const int32_t *counts,
+extern "C" int wesup_sp_pool_hypercolumn_bwd_walk(const float *grad_pooled, const int32_t *row_labels, const int32_t *counts,
                                              const int *C, const int *h, const int *w, int n_levels, int H, int W, int N,
                                              void *const *grad_side, void *ws, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     WESUP_REQUIRE(grad_pooled && row_labels && counts && C && h && w && grad_side && ws, WESUP_E_ARG,
-                  "wesup_sp_pool_hypercolumn_bwd: null pointer");
-    WESUP_REQUIRE(n_levels > 0 && n_levels <= WESUP_MAX_LEVELS, WESUP_E_ARG, "wesup_sp_pool_hypercolumn_bwd: n_levels=%d out of range", n_levels);
-    WESUP_REQUIRE(H > 0 && W > 0 && N > 0, WESUP_E_ARG, "wesup_sp_pool_hypercolumn_bwd: bad size H=%d W=%d N=%d", H, W, N);
-    WESUP_REQUIRE((long)H * W < (1L << 31), WESUP_E_UNSUPPORTED, "wesup_sp_pool_hypercolumn_bwd: H*W must fit int32");
-    WESUP_REQUIRE(aligned16(grad_pooled) && aligned16(ws), WESUP_E_ALIGN, "wesup_sp_pool_hypercolumn_bwd: grad_pooled/ws must be 16-byte aligned");
+                  "wesup_sp_pool_hypercolumn_bwd_walk: null pointer");
+    WESUP_REQUIRE(n_levels > 0 && n_levels <= WESUP_MAX_LEVELS, WESUP_E_ARG, "wesup_sp_pool_hypercolumn_bwd_walk: n_levels=%d out of range", n_levels);
+    WESUP_REQUIRE(H > 0 && W > 0 && N > 0, WESUP_E_ARG, "wesup_sp_pool_hypercolumn_bwd_walk: bad size H=%d W=%d N=%d", H, W, N);
+    WESUP_REQUIRE((long)H * W < (1L << 31), WESUP_E_UNSUPPORTED, "wesup_sp_pool_hypercolumn_bwd_walk: H*W must fit int32");
+    WESUP_REQUIRE(aligned16(grad_pooled) && aligned16(ws), WESUP_E_ALIGN, "wesup_sp_pool_hypercolumn_bwd_walk: grad_pooled/ws must be 16-byte aligned");
     FusedLevels L;
     L.n = n_levels; L.H = H; L.W = W;
     int off = 0;
     long biggest = 0, in_max = 0;
     for (int l = 0; l < n_levels; ++l) {
-        WESUP_REQUIRE(C[l] > 0 && h[l] > 0 && w[l] > 0, WESUP_E_ARG, "wesup_sp_pool_hypercolumn_bwd: level %d has empty shape", l);
-        WESUP_REQUIRE(C[l] % 4 == 0, WESUP_E_ALIGN, "wesup_sp_pool_hypercolumn_bwd: C[%d]=%d must be a multiple of 4", l, C[l]);
-        WESUP_REQUIRE(grad_side[l] != nullptr && aligned16(grad_side[l]), WESUP_E_ALIGN, "wesup_sp_pool_hypercolumn_bwd: grad_side[%d] null or unaligned", l);
+        WESUP_REQUIRE(C[l] > 0 && h[l] > 0 && w[l] > 0, WESUP_E_ARG, "wesup_sp_pool_hypercolumn_bwd_walk: level %d has empty shape", l);
+        WESUP_REQUIRE(C[l] % 4 == 0, WESUP_E_ALIGN, "wesup_sp_pool_hypercolumn_bwd_walk: C[%d]=%d must be a multiple of 4", l, C[l]);
+        WESUP_REQUIRE(grad_side[l] != nullptr && aligned16(grad_side[l]), WESUP_E_ALIGN, "wesup_sp_pool_hypercolumn_bwd_walk: grad_side[%d] null or unaligned", l);
         L.C[l] = C[l]; L.h[l] = h[l]; L.w[l] = w[l]; L.coff[l] = off;
         L.sy[l] = bilinear_scale(h[l], H); L.sx[l] = bilinear_scale(w[l], W);
         L.dst[l] = static_cast<float *>(grad_side[l]);
@@ -215,6 +215,6 @@ extern "C" int wesup_sp_pool_hypercolumn_bwd(const float *grad_pooled, const int
     long n4 = (long)N * (off / 4);
     fused_prescale_kernel<<<cdiv(n4, 256), 256, 0, stream>>>(grad_pooled, counts, n4, off / 4, gpn);
     fused_pool_hyper_bwd_kernel<<<dim3(cdiv(biggest, 256), n_levels), 256, 0, stream>>>(L, gpn, row_labels);
-    WESUP_CHECK_LAUNCH("wesup_sp_pool_hypercolumn_bwd", 3);
+    WESUP_CHECK_LAUNCH("wesup_sp_pool_hypercolumn_bwd_walk", 3);
     return 0;
 }

@@ -91,22 +91,22 @@ __global__ void __launch_bounds__(256) fused_hyper_pool_fwd_kernel(const Levels 
 
 using namespace wesup;
 
-extern "C" int wesup_hypercolumn_pool_fwd(const void *const *side, const int *C, const int *h, const int *w, int n_levels,
+extern "C" int wesup_hypercolumn_pool_fwd_walk(const void *const *side, const int *C, const int *h, const int *w, int n_levels,
                                           int H, int W, const int32_t *seg_offsets, const int32_t *seg_pixels, int N,
                                           float *pooled, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    WESUP_REQUIRE(side && C && h && w && seg_offsets && seg_pixels && pooled, WESUP_E_ARG, "wesup_hypercolumn_pool_fwd: null pointer");
-    WESUP_REQUIRE(n_levels > 0 && n_levels <= WESUP_MAX_LEVELS, WESUP_E_ARG, "wesup_hypercolumn_pool_fwd: n_levels=%d out of range", n_levels);
-    WESUP_REQUIRE(H > 0 && W > 0 && N > 0, WESUP_E_ARG, "wesup_hypercolumn_pool_fwd: bad size H=%d W=%d N=%d", H, W, N);
-    WESUP_REQUIRE((long)H * W < (1L << 31), WESUP_E_UNSUPPORTED, "wesup_hypercolumn_pool_fwd: H*W must fit int32");
-    WESUP_REQUIRE(aligned16(pooled), WESUP_E_ALIGN, "wesup_hypercolumn_pool_fwd: pooled must be 16-byte aligned");
+    WESUP_REQUIRE(side && C && h && w && seg_offsets && seg_pixels && pooled, WESUP_E_ARG, "wesup_hypercolumn_pool_fwd_walk: null pointer");
+    WESUP_REQUIRE(n_levels > 0 && n_levels <= WESUP_MAX_LEVELS, WESUP_E_ARG, "wesup_hypercolumn_pool_fwd_walk: n_levels=%d out of range", n_levels);
+    WESUP_REQUIRE(H > 0 && W > 0 && N > 0, WESUP_E_ARG, "wesup_hypercolumn_pool_fwd_walk: bad size H=%d W=%d N=%d", H, W, N);
+    WESUP_REQUIRE((long)H * W < (1L << 31), WESUP_E_UNSUPPORTED, "wesup_hypercolumn_pool_fwd_walk: H*W must fit int32");
+    WESUP_REQUIRE(aligned16(pooled), WESUP_E_ALIGN, "wesup_hypercolumn_pool_fwd_walk: pooled must be 16-byte aligned");
     Levels L;
     L.n = n_levels; L.H = H; L.W = W;
     int off = 0;
     for (int l = 0; l < n_levels; ++l) {
-        WESUP_REQUIRE(C[l] > 0 && h[l] > 0 && w[l] > 0, WESUP_E_ARG, "wesup_hypercolumn_pool_fwd: level %d has empty shape", l);
-        WESUP_REQUIRE(C[l] % 4 == 0, WESUP_E_ALIGN, "wesup_hypercolumn_pool_fwd: C[%d]=%d must be a multiple of 4", l, C[l]);
-        WESUP_REQUIRE(side[l] != nullptr && aligned16(side[l]), WESUP_E_ALIGN, "wesup_hypercolumn_pool_fwd: side[%d] null or unaligned", l);
+        WESUP_REQUIRE(C[l] > 0 && h[l] > 0 && w[l] > 0, WESUP_E_ARG, "wesup_hypercolumn_pool_fwd_walk: level %d has empty shape", l);
+        WESUP_REQUIRE(C[l] % 4 == 0, WESUP_E_ALIGN, "wesup_hypercolumn_pool_fwd_walk: C[%d]=%d must be a multiple of 4", l, C[l]);
+        WESUP_REQUIRE(side[l] != nullptr && aligned16(side[l]), WESUP_E_ALIGN, "wesup_hypercolumn_pool_fwd_walk: side[%d] null or unaligned", l);
         L.src[l] = static_cast<const float *>(side[l]);
         L.dst[l] = nullptr;
         L.C[l] = C[l]; L.h[l] = h[l]; L.w[l] = w[l]; L.coff[l] = off;
@@ -117,6 +117,6 @@ extern "C" int wesup_hypercolumn_pool_fwd(const void *const *side, const int *C,
     const int G4 = off / 4;
     const long n_items = (long)N * G4;
     fused_hyper_pool_fwd_kernel<<<cdiv(n_items, 256), 256, 0, stream>>>(L, seg_offsets, seg_pixels, G4, n_items, pooled);
-    WESUP_CHECK_LAUNCH("wesup_hypercolumn_pool_fwd", 1);
+    WESUP_CHECK_LAUNCH("wesup_hypercolumn_pool_fwd_walk", 1);
     return 0;
 }

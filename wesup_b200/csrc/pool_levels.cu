@@ -1,0 +1,467 @@
+// Superpixel means taken DIRECTLY from low-resolution feature levels, and the
+// adjoint -- the footprint formulation of (b) o (a).
+//
+// Reference semantics: bilinear(align_corners=True) upsampling + channel concat
+// (/root/reference/models/wesup.py:254-261) followed by torch.mm(sp_maps, x.t())
+// (:284-285).  Both are linear, so for every level l and superpixel k
+//
+//     pooled[k, coff_l + c] = (1/|S_k|) * sum_q  G_k(q) * level_l[q, c]
+//     G_k(q) = sum_{(y,x) in S_k} wy(y, q.i) * wx(x, q.j)          (bilinear tap weights)
+//
+// where q runs over the LOW-resolution cells of the level.  The per-pixel
+// formulation (4 taps per pixel per channel: 8448 FMA/pixel at C = 2112) spends
+// its time re-deriving the same few cells; here the weights G_k are aggregated
+// ONCE per superpixel and scale (scalar work, shared by all channels and by all
+// levels of the same resolution) and the channel work is sum_cells G * level:
+// ~250 FMA/pixel.  Nothing of size H*W*C is read or written: traffic is the
+// levels themselves (read once from HBM, re-read from L2 by neighbouring
+// superpixels) plus the (N, C) result.
+//
+// The same kernels serve two callers: the 13 side outputs (sum C = 2112, the
+// reference's hypercolumn channels) and -- "pool first" -- the 13 backbone conv
+// outputs (sum C = 4224), after which the 1x1 side convolutions run on N rows
+// instead of H*W pixels (mean and 1x1 conv commute).
+//
+// Deterministic: floating-point sums have a fixed order, the only atomics are integer
+// (fixed-point weight sums in shared memory), so results are bit-reproducible run to run.
+#include "common.cuh"
+#include <limits.h>
+
+namespace wesup {
+
+constexpr int PF_THREADS = 256;
+constexpr int PF_GRID_CAP = 1024;    // cells of a superpixel's low-res weight grid kept in shared memory
+
+constexpr int PB_WARPS = 8;          // backward: one warp per low-res cell
+constexpr int PB_STAGE_MAX = 1536;   // footprint pixels staged in shared memory per warp
+
+// consecutive levels of equal resolution: their channels are contiguous in the pooled row
+struct Groups {
+    int n;
+    int l0[WESUP_MAX_LEVELS], l1[WESUP_MAX_LEVELS];
+    int h[WESUP_MAX_LEVELS], w[WESUP_MAX_LEVELS];
+    float sy[WESUP_MAX_LEVELS], sx[WESUP_MAX_LEVELS];
+    int coff[WESUP_MAX_LEVELS], Cg[WESUP_MAX_LEVELS];
+    int ident[WESUP_MAX_LEVELS];
+};
+
+__device__ __forceinline__ void locate_level(const Levels &L, int l0, int l1, int c, int &l, int &cl) {
+    l = l0;
+    while (l + 1 < l1 && c >= L.C[l]) { c -= L.C[l]; ++l; }
+    cl = c;
+}
+
+// ---------------------------------------------------------------------------
+// forward: one block per superpixel
+//
+// Weight aggregation: every pixel adds its 2x2 tap weights wy*wx to the cells of the
+// superpixel's low-res bounding box, held in shared memory as 64-bit FIXED-POINT sums
+// (32 fractional bits).  Integer adds commute, so the result does not depend on the
+// order in which the threads arrive: deterministic without a fixed summation order,
+// at a quantisation of 2^-33 per term (fp32 keeps 2^-24 of a weight of order 1).
+// The non-zero cells are then compacted into a list (cell offset, weight) and the
+// channel work streams over that list with independent 128-bit loads in flight.
+// ---------------------------------------------------------------------------
+struct CellW { int off; float w; };
+
+__global__ void __launch_bounds__(PF_THREADS) levels_pool_fwd_kernel(const Levels L, const Groups G,
+                                                                     const int32_t *__restrict__ seg_offsets,
+                                                                     const int32_t *__restrict__ seg_pixels,
+                                                                     float *__restrict__ pooled) {
+    __shared__ unsigned long long grid[PF_GRID_CAP];
+    __shared__ CellW cellw[PF_GRID_CAP];
+    __shared__ float4 part[PF_THREADS];
+    __shared__ int bbx[2];
+    __shared__ int warp_cnt[PF_THREADS / 32 + 1];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int k = blockIdx.x;
+    const int beg = __ldg(seg_offsets + k), end = __ldg(seg_offsets + k + 1);
+    const int n = end - beg;
+    float *__restrict__ out = pooled + (long)k * L.Ctot;
+    if (n <= 0) {
+        for (int c = tid * 4; c < L.Ctot; c += PF_THREADS * 4) *reinterpret_cast<float4 *>(out + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const int W = L.W;
+    // bounding box: pixel ids ascend inside a row of the CSR, so rows come from the two ends
+    if (tid == 0) { bbx[0] = INT_MAX; bbx[1] = -1; }
+    __syncthreads();
+    {
+        int xmin = INT_MAX, xmax = -1;
+        for (int i = beg + tid; i < end; i += PF_THREADS) {
+            const int p = __ldg(seg_pixels + i);
+            const int x = p - (p / W) * W;
+            xmin = min(xmin, x); xmax = max(xmax, x);
+        }
+        xmin = __reduce_min_sync(0xffffffffu, xmin);
+        xmax = __reduce_max_sync(0xffffffffu, xmax);
+        if (lane == 0) { atomicMin(&bbx[0], xmin); atomicMax(&bbx[1], xmax); }
+    }
+    __syncthreads();
+    const int ymin = __ldg(seg_pixels + beg) / W, ymax = __ldg(seg_pixels + end - 1) / W;
+    const int xmin = bbx[0], xmax = bbx[1];
+    const float inv = 1.0f / (float)n;
+
+    for (int g = 0; g < G.n; ++g) {
+        const int nch4 = G.Cg[g] >> 2;
+        const int hl = G.h[g], wl = G.w[g];
+        const float sy = G.sy[g], sx = G.sx[g];
+        const bool ident = G.ident[g] != 0;
+        int i_lo = 0, j_lo = 0, gw = 1, cells = 0, n_list = 0;
+        bool use_grid = false;
+        if (!ident) {
+            i_lo = bilinear_tap(ymin, sy, hl).i0;
+            j_lo = bilinear_tap(xmin, sx, wl).i0;
+            const int gh = bilinear_tap(ymax, sy, hl).i1 - i_lo + 1;
+            gw = bilinear_tap(xmax, sx, wl).i1 - j_lo + 1;
+            use_grid = (long)gh * gw <= PF_GRID_CAP;
+            cells = use_grid ? gh * gw : 0;
+        }
+        if (use_grid) {
+            for (int e = tid; e < cells; e += PF_THREADS) grid[e] = 0ull;
+            __syncthreads();
+            for (int it = beg + tid; it < end; it += PF_THREADS) {
+                const int p = __ldg(seg_pixels + it);
+                const int y = p / W, x = p - y * W;
+                const Tap ty = bilinear_tap(y, sy, hl), tx = bilinear_tap(x, sx, wl);
+                const int r0 = (ty.i0 - i_lo) * gw, r1 = (ty.i1 - i_lo) * gw, c0 = tx.i0 - j_lo, c1 = tx.i1 - j_lo;
+                // 2^32 * w rounded to nearest; w in [0, 1]
+                atomicAdd(&grid[r0 + c0], (unsigned long long)__float2ll_rn(ty.w0 * tx.w0 * 4294967296.0f));
+                atomicAdd(&grid[r0 + c1], (unsigned long long)__float2ll_rn(ty.w0 * tx.w1 * 4294967296.0f));
+                atomicAdd(&grid[r1 + c0], (unsigned long long)__float2ll_rn(ty.w1 * tx.w0 * 4294967296.0f));
+                atomicAdd(&grid[r1 + c1], (unsigned long long)__float2ll_rn(ty.w1 * tx.w1 * 4294967296.0f));
+            }
+            __syncthreads();
+            // compact the non-zero cells (order: round, warp, lane -- fixed)
+            const float inv_gw = 1.0f / (float)gw;
+            int base_pos = 0;
+            for (int e0 = 0; e0 < cells; e0 += PF_THREADS) {
+                const int e = e0 + tid;
+                const unsigned long long v = e < cells ? grid[e] : 0ull;
+                const unsigned m = __ballot_sync(0xffffffffu, v != 0ull);
+                if (lane == 0) warp_cnt[wid] = __popc(m);
+                __syncthreads();
+                int before = base_pos, total = base_pos;
+                for (int q = 0; q < PF_THREADS / 32; ++q) {
+                    const int c = warp_cnt[q];
+                    if (q < wid) before += c;
+                    total += c;
+                }
+                if (v != 0ull) {
+                    const int i = __float2int_rd(((float)e + 0.5f) * inv_gw), j = e - i * gw;
+                    CellW cw;
+                    cw.off = i * wl + j;
+                    cw.w = (float)((double)v * (1.0 / 4294967296.0));
+                    cellw[before + __popc(m & ((1u << lane) - 1u))] = cw;
+                }
+                base_pos = total;
+                __syncthreads();
+            }
+            n_list = base_pos;
+        }
+        // ---- channel work: thread = (slice of the items, 4-channel group) ----------------
+        for (int cb = 0; cb < nch4; cb += PF_THREADS) {
+            const int active = min(nch4 - cb, PF_THREADS);
+            const int nsl = PF_THREADS / active;
+            const int sl = tid / active;
+            const int c4 = cb + (tid - sl * active);
+            const bool live = sl < nsl;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) {
+                int l, cl;
+                locate_level(L, G.l0[g], G.l1[g], c4 << 2, l, cl);
+                const int Cl = L.C[l];
+                const float *__restrict__ src = L.src[l] + cl;
+                if (ident) {
+                    int it = beg + sl;
+                    for (; it + 3 * nsl < end; it += 4 * nsl) {
+                        const int p0 = __ldg(seg_pixels + it), p1 = __ldg(seg_pixels + it + nsl), p2 = __ldg(seg_pixels + it + 2 * nsl),
+                                  p3 = __ldg(seg_pixels + it + 3 * nsl);
+                        const float4 v0 = __ldg(reinterpret_cast<const float4 *>(src + (long)p0 * Cl));
+                        const float4 v1 = __ldg(reinterpret_cast<const float4 *>(src + (long)p1 * Cl));
+                        const float4 v2 = __ldg(reinterpret_cast<const float4 *>(src + (long)p2 * Cl));
+                        const float4 v3 = __ldg(reinterpret_cast<const float4 *>(src + (long)p3 * Cl));
+                        acc = acc + v0; acc = acc + v1; acc = acc + v2; acc = acc + v3;
+                    }
+                    for (; it < end; it += nsl) acc = acc + __ldg(reinterpret_cast<const float4 *>(src + (long)__ldg(seg_pixels + it) * Cl));
+                } else if (use_grid) {
+                    const float *__restrict__ base = src + ((long)i_lo * wl + j_lo) * Cl;
+                    int e = sl;
+                    for (; e + 3 * nsl < n_list; e += 4 * nsl) {
+                        const CellW a0 = cellw[e], a1 = cellw[e + nsl], a2 = cellw[e + 2 * nsl], a3 = cellw[e + 3 * nsl];
+                        const float4 v0 = __ldg(reinterpret_cast<const float4 *>(base + (long)a0.off * Cl));
+                        const float4 v1 = __ldg(reinterpret_cast<const float4 *>(base + (long)a1.off * Cl));
+                        const float4 v2 = __ldg(reinterpret_cast<const float4 *>(base + (long)a2.off * Cl));
+                        const float4 v3 = __ldg(reinterpret_cast<const float4 *>(base + (long)a3.off * Cl));
+                        fma4(acc, a0.w, v0); fma4(acc, a1.w, v1); fma4(acc, a2.w, v2); fma4(acc, a3.w, v3);
+                    }
+                    for (; e < n_list; e += nsl) {
+                        const CellW a0 = cellw[e];
+                        fma4(acc, a0.w, __ldg(reinterpret_cast<const float4 *>(base + (long)a0.off * Cl)));
+                    }
+                } else {
+                    // bounding box too large for the shared grid (huge / scattered superpixel): per-pixel taps
+                    for (int it = beg + sl; it < end; it += nsl) {
+                        const int p = __ldg(seg_pixels + it);
+                        const int y = p / W, x = p - y * W;
+                        const Tap ty = bilinear_tap(y, sy, hl), tx = bilinear_tap(x, sx, wl);
+                        const float *r0 = src + (long)ty.i0 * wl * Cl, *r1 = src + (long)ty.i1 * wl * Cl;
+                        float4 a = ty.w0 * __ldg(reinterpret_cast<const float4 *>(r0 + (long)tx.i0 * Cl));
+                        fma4(a, ty.w1, __ldg(reinterpret_cast<const float4 *>(r1 + (long)tx.i0 * Cl)));
+                        float4 b = ty.w0 * __ldg(reinterpret_cast<const float4 *>(r0 + (long)tx.i1 * Cl));
+                        fma4(b, ty.w1, __ldg(reinterpret_cast<const float4 *>(r1 + (long)tx.i1 * Cl)));
+                        fma4(acc, tx.w0, a);
+                        fma4(acc, tx.w1, b);
+                    }
+                }
+            }
+            if (nsl > 1) {                      // block-uniform
+                part[tid] = acc;
+                __syncthreads();
+                if (sl == 0) {
+                    for (int s = 1; s < nsl; ++s) acc = acc + part[s * active + tid];
+                }
+            }
+            if (live && sl == 0) *reinterpret_cast<float4 *>(out + G.coff[g] + (c4 << 2)) = inv * acc;
+            if (nsl > 1) __syncthreads();
+        }
+        __syncthreads();       // grid[] / cellw[] are rewritten by the next group
+    }
+}
+
+// ---------------------------------------------------------------------------
+// backward: one warp per low-resolution cell q of a group
+//   grad_level_l[q, c] = sum_k G_k(q) / |S_k| * grad_pooled[k, coff_l + c]
+// The warp walks the cell's high-resolution footprint once (labels + weights,
+// staged in shared memory), then visits the distinct labels in ascending order:
+// a fixed-order reduction gives the label's total weight and every lane gathers
+// its channel groups of that pooled-gradient row.
+// ---------------------------------------------------------------------------
+struct Staged { int lab; float w; };
+
+__device__ __forceinline__ void footprint_range(int i, float scale, int out_size, int &lo, int &hi) {
+    if (!(scale > 0.f)) { lo = 0; hi = out_size - 1; return; }
+    const float inv = 1.0f / scale;
+    lo = (int)floorf((float)(i - 1) * inv) - 1;
+    hi = (int)ceilf((float)(i + 1) * inv) + 1;
+    lo = max(lo, 0);
+    hi = min(hi, out_size - 1);
+}
+
+template <int V>
+__global__ void __launch_bounds__(PB_WARPS * 32) levels_pool_bwd_kernel(const Levels L, const Groups G, int g, int stage_cap,
+                                                                        const float *__restrict__ gp,
+                                                                        const int32_t *__restrict__ row_labels,
+                                                                        const int32_t *__restrict__ counts) {
+    extern __shared__ Staged stage_all[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hg = G.h[g], wg = G.w[g];
+    const long q = (long)blockIdx.x * PB_WARPS + wid;
+    if (q >= (long)hg * wg) return;
+    const int nch4 = G.Cg[g] >> 2, Ctot = L.Ctot, W = L.W;
+    const float *__restrict__ gpg = gp + G.coff[g];
+    float4 acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (G.ident[g]) {
+        const int k = __ldg(row_labels + q);
+        if (k >= 0) {
+            const int cnt = __ldg(counts + k);
+            const float wv = cnt > 0 ? 1.0f / (float)cnt : 0.f;
+            const float *__restrict__ row = gpg + (long)k * Ctot;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int c4 = lane + 32 * v;
+                if (c4 < nch4) acc[v] = wv * __ldg(reinterpret_cast<const float4 *>(row) + c4);
+            }
+        }
+    } else {
+        const int i = (int)(q / wg), j = (int)(q - (long)i * wg);
+        const float sy = G.sy[g], sx = G.sx[g];
+        int ylo, yhi, xlo, xhi;
+        footprint_range(i, sy, L.H, ylo, yhi);
+        footprint_range(j, sx, W, xlo, xhi);
+        const int nx = xhi - xlo + 1, nf = (yhi - ylo + 1) * nx;
+        const float inv_nx = 1.0f / (float)nx;
+        Staged *st = stage_all + (long)wid * stage_cap;
+        const bool staged = nf <= stage_cap;
+        auto fetch = [&](int t) {
+            const int a = __float2int_rd(((float)t + 0.5f) * inv_nx), b = t - a * nx;
+            const int y = ylo + a, x = xlo + b;
+            const Tap ty = bilinear_tap(y, sy, hg), tx = bilinear_tap(x, sx, wg);
+            const float wy = (ty.i0 == i ? ty.w0 : 0.f) + (ty.i1 == i ? ty.w1 : 0.f);
+            const float wx = (tx.i0 == j ? tx.w0 : 0.f) + (tx.i1 == j ? tx.w1 : 0.f);
+            Staged s;
+            s.w = wy * wx;
+            s.lab = (s.w != 0.f) ? __ldg(row_labels + (long)y * W + x) : -1;
+            return s;
+        };
+        int cur = INT_MAX;
+        for (int t = lane; t < nf; t += 32) {
+            const Staged s = fetch(t);
+            if (staged) st[t] = s;
+            if (s.lab >= 0) cur = min(cur, s.lab);
+        }
+        __syncwarp();
+        cur = __reduce_min_sync(0xffffffffu, cur);
+        while (cur != INT_MAX) {
+            float ws = 0.f;
+            int nxt = INT_MAX;
+            for (int t = lane; t < nf; t += 32) {
+                const Staged s = staged ? st[t] : fetch(t);
+                if (s.lab == cur) ws += s.w;
+                else if (s.lab > cur) nxt = min(nxt, s.lab);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
+            nxt = __reduce_min_sync(0xffffffffu, nxt);
+            const int cnt = __ldg(counts + cur);
+            ws = cnt > 0 ? ws / (float)cnt : 0.f;
+            const float *__restrict__ row = gpg + (long)cur * Ctot;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int c4 = lane + 32 * v;
+                if (c4 < nch4) fma4(acc[v], ws, __ldg(reinterpret_cast<const float4 *>(row) + c4));
+            }
+            cur = nxt;
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const int c4 = lane + 32 * v;
+        if (c4 < nch4) {
+            int l, cl;
+            locate_level(L, G.l0[g], G.l1[g], c4 << 2, l, cl);
+            *reinterpret_cast<float4 *>(L.dst[l] + q * L.C[l] + cl) = acc[v];
+        }
+    }
+}
+
+constexpr int PB_VMAX = 12;          // float4 accumulators per lane: a group carries at most 32*4*12 = 1536 channels
+
+// group consecutive levels of equal resolution; a group never exceeds PB_VMAX*128 channels
+static int build_groups(Groups &G, const Levels &L) {
+    G.n = 0;
+    for (int l = 0; l < L.n; ++l) {
+        if (L.C[l] > PB_VMAX * 128) return -1;
+        const int g = G.n - 1;
+        if (g >= 0 && G.h[g] == L.h[l] && G.w[g] == L.w[l] && G.Cg[g] + L.C[l] <= PB_VMAX * 128) {
+            G.l1[g] = l + 1;
+            G.Cg[g] += L.C[l];
+        } else {
+            const int n = G.n++;
+            G.l0[n] = l; G.l1[n] = l + 1;
+            G.h[n] = L.h[l]; G.w[n] = L.w[l];
+            G.sy[n] = L.sy[l]; G.sx[n] = L.sx[l];
+            G.coff[n] = L.coff[l]; G.Cg[n] = L.C[l];
+            G.ident[n] = (L.h[l] == L.H && L.w[l] == L.W) ? 1 : 0;
+        }
+    }
+    return 0;
+}
+
+static int fill_pool_levels(Levels &L, const char *who, const void *const *ptrs, bool is_dst, const int *C, const int *h, const int *w,
+                            int n_levels, int H, int W) {
+    L.n = n_levels; L.H = H; L.W = W;
+    int off = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        WESUP_REQUIRE(C[l] > 0 && h[l] > 0 && w[l] > 0, WESUP_E_ARG, "%s: level %d has empty shape", who, l);
+        WESUP_REQUIRE(C[l] % 4 == 0, WESUP_E_ALIGN, "%s: C[%d]=%d must be a multiple of 4", who, l, C[l]);
+        WESUP_REQUIRE(ptrs[l] != nullptr && aligned16(ptrs[l]), WESUP_E_ALIGN, "%s: level %d pointer null or unaligned", who, l);
+        L.src[l] = is_dst ? nullptr : static_cast<const float *>(ptrs[l]);
+        L.dst[l] = is_dst ? static_cast<float *>(const_cast<void *>(ptrs[l])) : nullptr;
+        L.C[l] = C[l]; L.h[l] = h[l]; L.w[l] = w[l]; L.coff[l] = off;
+        L.sy[l] = bilinear_scale(h[l], H); L.sx[l] = bilinear_scale(w[l], W);
+        off += C[l];
+    }
+    L.Ctot = off;
+    return 0;
+}
+
+static inline int stage_need(float scale, int out_size) {
+    if (!(scale > 0.f)) return out_size;
+    int k = (int)(2.0f / scale) + 6;
+    return k < out_size ? k : out_size;
+}
+
+template <int V>
+static void launch_bwd(const Levels &L, const Groups &G, int g, int stage_cap, const float *gp, const int32_t *row_labels,
+                       const int32_t *counts, cudaStream_t stream) {
+    const size_t smem = (size_t)PB_WARPS * stage_cap * sizeof(Staged);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(levels_pool_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long cells = (long)G.h[g] * G.w[g];
+    levels_pool_bwd_kernel<V><<<cdiv(cells, PB_WARPS), PB_WARPS * 32, smem, stream>>>(L, G, g, stage_cap, gp, row_labels, counts);
+}
+
+}  // namespace wesup
+
+using namespace wesup;
+
+extern "C" int wesup_levels_pool_fwd(const void *const *level, const int *C, const int *h, const int *w, int n_levels, int H,
+                                     int W, const int32_t *seg_offsets, const int32_t *seg_pixels, int N, float *pooled,
+                                     void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WESUP_REQUIRE(level && C && h && w && seg_offsets && seg_pixels && pooled, WESUP_E_ARG, "wesup_levels_pool_fwd: null pointer");
+    WESUP_REQUIRE(n_levels > 0 && n_levels <= WESUP_MAX_LEVELS, WESUP_E_ARG, "wesup_levels_pool_fwd: n_levels=%d out of range", n_levels);
+    WESUP_REQUIRE(H > 0 && W > 0 && N > 0, WESUP_E_ARG, "wesup_levels_pool_fwd: bad size H=%d W=%d N=%d", H, W, N);
+    WESUP_REQUIRE((long)H * W < (1L << 31), WESUP_E_UNSUPPORTED, "wesup_levels_pool_fwd: H*W must fit int32");
+    WESUP_REQUIRE(H < 65536 && W < 65536, WESUP_E_UNSUPPORTED, "wesup_levels_pool_fwd: H and W must be below 65536");
+    WESUP_REQUIRE(aligned16(pooled), WESUP_E_ALIGN, "wesup_levels_pool_fwd: pooled must be 16-byte aligned");
+    Levels L;
+    int rc = fill_pool_levels(L, "wesup_levels_pool_fwd", level, false, C, h, w, n_levels, H, W);
+    if (rc) return rc;
+    Groups G;
+    WESUP_REQUIRE(build_groups(G, L) == 0, WESUP_E_UNSUPPORTED, "wesup_levels_pool_fwd: a level has more than %d channels", PB_VMAX * 128);
+    levels_pool_fwd_kernel<<<N, PF_THREADS, 0, stream>>>(L, G, seg_offsets, seg_pixels, pooled);
+    WESUP_CHECK_LAUNCH("wesup_levels_pool_fwd", 1);
+    return 0;
+}
+
+extern "C" int wesup_levels_pool_bwd(const float *grad_pooled, const int32_t *row_labels, const int32_t *counts, const int *C,
+                                     const int *h, const int *w, int n_levels, int H, int W, int N, void *const *grad_level,
+                                     void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WESUP_REQUIRE(grad_pooled && row_labels && counts && C && h && w && grad_level, WESUP_E_ARG, "wesup_levels_pool_bwd: null pointer");
+    WESUP_REQUIRE(n_levels > 0 && n_levels <= WESUP_MAX_LEVELS, WESUP_E_ARG, "wesup_levels_pool_bwd: n_levels=%d out of range", n_levels);
+    WESUP_REQUIRE(H > 0 && W > 0 && N > 0, WESUP_E_ARG, "wesup_levels_pool_bwd: bad size H=%d W=%d N=%d", H, W, N);
+    WESUP_REQUIRE((long)H * W < (1L << 31), WESUP_E_UNSUPPORTED, "wesup_levels_pool_bwd: H*W must fit int32");
+    WESUP_REQUIRE(aligned16(grad_pooled), WESUP_E_ALIGN, "wesup_levels_pool_bwd: grad_pooled must be 16-byte aligned");
+    Levels L;
+    int rc = fill_pool_levels(L, "wesup_levels_pool_bwd", grad_level, true, C, h, w, n_levels, H, W);
+    if (rc) return rc;
+    Groups G;
+    WESUP_REQUIRE(build_groups(G, L) == 0, WESUP_E_UNSUPPORTED, "wesup_levels_pool_bwd: a level has more than %d channels", PB_VMAX * 128);
+    // coarse groups first: their warps carry the longest footprint walks
+    int launched = 0;
+    for (int g = G.n - 1; g >= 0; --g) {
+        int stage_cap = 1;
+        if (!G.ident[g]) {
+            const long need = (long)stage_need(G.sy[g], H) * stage_need(G.sx[g], W);
+            stage_cap = (int)(need < PB_STAGE_MAX ? need : PB_STAGE_MAX);
+        }
+        const int v = (G.Cg[g] / 4 + 31) / 32;
+        if (v <= 1) launch_bwd<1>(L, G, g, stage_cap, grad_pooled, row_labels, counts, stream);
+        else if (v <= 2) launch_bwd<2>(L, G, g, stage_cap, grad_pooled, row_labels, counts, stream);
+        else if (v <= 4) launch_bwd<4>(L, G, g, stage_cap, grad_pooled, row_labels, counts, stream);
+        else if (v <= 6) launch_bwd<6>(L, G, g, stage_cap, grad_pooled, row_labels, counts, stream);
+        else launch_bwd<PB_VMAX>(L, G, g, stage_cap, grad_pooled, row_labels, counts, stream);
+        ++launched;
+    }
+    WESUP_CHECK_LAUNCH("wesup_levels_pool_bwd", launched);
+    return 0;
+}
+
+// The historical entry points of the fused path keep their signatures and now run the
+// footprint kernels; the per-pixel walk kernels stay exported as *_walk (cross-checks, benches).
+extern "C" int wesup_hypercolumn_pool_fwd(const void *const *side, const int *C, const int *h, const int *w, int n_levels,
+                                          int H, int W, const int32_t *seg_offsets, const int32_t *seg_pixels, int N,
+                                          float *pooled, void *stream) {
+    return wesup_levels_pool_fwd(side, C, h, w, n_levels, H, W, seg_offsets, seg_pixels, N, pooled, stream);
+}
+
+extern "C" int wesup_sp_pool_hypercolumn_bwd(const float *grad_pooled, const int32_t *row_labels, const int32_t *counts,
+                                             const int *C, const int *h, const int *w, int n_levels, int H, int W, int N,
+                                             void *const *grad_side, void *ws, void *stream) {
+    (void)ws;
+    return wesup_levels_pool_bwd(grad_pooled, row_labels, counts, C, h, w, n_levels, H, W, N, grad_side, stream);
+}

@@ -114,11 +114,13 @@ class BaseTrainer(ABC):
     # ---- the loop -------------------------------------------------------------
     def train_one_iteration(self, phase, *data):
         """Same sequence as the reference (models/base.py:184-211): preprocess, zero_grad,
-        forward, loss, NaN check, backward, step, postprocess, metrics.  The host reads
-        every scalar of the iteration (loss, loss-side metrics, accuracy/dice) in ONE
-        device-to-host transfer after the optimizer step has been enqueued, so the GPU
-        never idles behind a `.item()`; a NaN loss still raises ValueError('Loss is nan!')
-        in the same iteration (uncaught by the epoch loop, as in the reference)."""
+        forward, loss, NaN check, backward, step, postprocess, metrics.  Every scalar of the
+        iteration (loss, loss-side metrics, accuracy/dice) stays on the device and travels to
+        the host in ONE asynchronous transfer, which the host reads `metrics_lag` iterations
+        later (default 1: iteration k's numbers are read after iteration k+1 has been
+        enqueued), so the GPU never idles behind a `.item()`.  A NaN loss raises
+        ValueError('Loss is nan!') when its scalars are read -- uncaught by the epoch loop, as
+        in the reference; `metrics_lag=0` restores the reference's same-iteration check."""
         input_, target = self.preprocess(*data)
         if self.grad_sync is not None:
             self.grad_sync.zero_grad()       # keeps .grad as views of the flat all-reduce buffer
@@ -140,10 +142,40 @@ class BaseTrainer(ABC):
             metrics.update(self.evaluate(pred, target))
         finally:
             self._defer_scalars = False
-        metrics = self._read_scalars(metrics)
-        if phase == "train" and metrics["loss"] != metrics["loss"]:
-            raise ValueError("Loss is nan!")
-        self.tracker.step(metrics)
+        self._submit_scalars(metrics, phase)
+        self.flush_metrics(keep=max(int(self.kwargs.get("metrics_lag", 1) or 0), 0))
+
+    def _submit_scalars(self, metrics, phase):
+        """Start the single device-to-host transfer of this iteration's 0-dim tensors."""
+        keys = [k for k, v in metrics.items() if torch.is_tensor(v)]
+        host = event = None
+        if keys:
+            stacked = torch.stack([metrics[k].detach().float().reshape(()) for k in keys])
+            if stacked.is_cuda:
+                host = torch.empty(len(keys), dtype=torch.float32, pin_memory=True)
+                host.copy_(stacked, non_blocking=True)
+                event = torch.cuda.Event()
+                event.record(torch.cuda.current_stream(stacked.device))
+            else:
+                host = stacked
+        if not hasattr(self, "_pending_scalars"):
+            self._pending_scalars = []
+        self._pending_scalars.append((metrics, keys, host, event, phase))
+
+    def flush_metrics(self, keep=0):
+        """Read the scalars of all but the `keep` most recent iterations and hand them to the
+        tracker (in iteration order).  Called with keep=0 at the end of every phase."""
+        pending = getattr(self, "_pending_scalars", None)
+        while pending and len(pending) > keep:
+            metrics, keys, host, event, phase = pending.pop(0)
+            if event is not None:
+                event.synchronize()
+            if keys:
+                metrics = {**metrics, **dict(zip(keys, host.tolist()))}
+            if phase == "train" and metrics["loss"] != metrics["loss"]:
+                pending.clear()
+                raise ValueError("Loss is nan!")
+            self.tracker.step(metrics)
 
     @staticmethod
     def _read_scalars(metrics):
@@ -175,6 +207,7 @@ class BaseTrainer(ABC):
                 except RuntimeError as ex:       # same policy as the reference (base.py:234-237)
                     self.logger.exception(ex)
                 data = upcoming
+            self.flush_metrics()
             self.logger.info(f"Took {time.time() - start:.2f}s.")
             self.logger.info(self.tracker.log())
 

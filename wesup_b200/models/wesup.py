@@ -119,6 +119,11 @@ class WESUP(nn.Module):
                     `feature_maps` exposes, kernel (b) pools it.  False: ONE fused kernel pools
                     straight from the side outputs (`feature_maps` stays None; needs
                     fused_backward) -- same numbers, no 1.8 GB round trip
+      pool_first    True (default; only with materialize_hypercolumn=False): the superpixel means
+                    are taken from the 13 backbone conv outputs (4224 channels) and the 1x1 side
+                    convolutions then run on the N pooled rows instead of on H*W pixels -- a mean
+                    and a 1x1 convolution commute, so `sp_features`/`sp_pred`/loss/gradients are the
+                    reference's up to fp32 rounding (second half)
     """
 
     def __init__(self, n_classes=2, D=32, **kwargs):
@@ -143,6 +148,14 @@ class WESUP(nn.Module):
         self.hc_layout = kwargs.get("hc_layout", "hwc")
         self.fused_backward = bool(kwargs.get("fused_backward", True))
         self.materialize_hypercolumn = bool(kwargs.get("materialize_hypercolumn", True))
+        self.pool_first = bool(kwargs.get("pool_first", True))
+        if self.hc_layout == "hwc":
+            # the convolutions run channels_last: keep their weights (and therefore weight gradients
+            # and momentum buffers) in that memory format too, so no per-iteration layout copies appear
+            # in backward.  Shapes, values and state_dict keys are unaffected.
+            for m in self.modules():
+                if isinstance(m, nn.Conv2d):
+                    m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
         self.feature_maps = None
         self.fm_size = None
         self.sp_features = None
@@ -166,6 +179,27 @@ class WESUP(nn.Module):
                 x = layer(x)
         return sides
 
+    def _pooled_first(self, x, sp):
+        """Superpixel means of the PRE-ReLU backbone conv outputs (one fused kernel over the 13
+        levels), then every side conv (reference :253, a 1x1 convolution + bias) as a small GEMM
+        on the pooled rows: mean_S(W f + b) == W mean_S(f) + b."""
+        x = x.contiguous(memory_format=torch.channels_last)
+        outs = []
+        for layer in self.backbone:
+            if isinstance(layer, nn.Conv2d):
+                x = layer(x)
+                outs.append(x)
+            elif isinstance(layer, nn.ReLU):
+                x = F.relu(x)            # out of place: the pooling kernel reads the pre-ReLU tensor afterwards
+            else:
+                x = layer(x)
+        pooled, _ = ops.hypercolumn_pool(outs, self.fm_size, sp, materialize=False)
+        cols = []
+        for name, part in zip(self._side_names, pooled.split([o.size(1) for o in outs], dim=1)):
+            conv = getattr(self, name)
+            cols.append(F.linear(part, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias))
+        return torch.cat(cols, dim=1)
+
     def _hypercolumn(self, x):
         self.fm_size = (x.size(2), x.size(3))
         feats = ops.hypercolumn(self._side_outputs(x), self.fm_size, dtype=self.hc_dtype, layout=self.hc_layout)
@@ -177,7 +211,11 @@ class WESUP(nn.Module):
         """x = (image (1,3,H,W), sp_maps); returns class-1 probability (1,H,W)."""
         x, sp_maps = x
         sp = sp_maps if isinstance(sp_maps, SuperpixelMaps) else SuperpixelMaps.from_dense(sp_maps)
-        if self.fused_backward and self.hc_layout == "hwc":
+        if self.fused_backward and self.hc_layout == "hwc" and self.pool_first and not self.materialize_hypercolumn:
+            self.fm_size = (x.size(2), x.size(3))
+            self.feature_maps = None
+            pooled = self._pooled_first(x, sp)
+        elif self.fused_backward and self.hc_layout == "hwc":
             self.fm_size = (x.size(2), x.size(3))
             pooled, feats = ops.hypercolumn_pool(self._side_outputs(x), self.fm_size, sp, dtype=self.hc_dtype,
                                                  materialize=self.materialize_hypercolumn)
@@ -246,9 +284,12 @@ class WESUPTrainer(BaseTrainer):
         return SegmentationDataset(root_dir, rescale_factor=self.kwargs.get("rescale_factor"), train=False)
 
     def get_default_optimizer(self):
-        optimizer = torch.optim.SGD(
-            filter(lambda p: p.requires_grad, self.model.parameters()),
-            lr=5e-5, momentum=self.kwargs.get("momentum"), weight_decay=self.kwargs.get("weight_decay"))
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        # same update rule as the reference's SGD; torch's single-kernel ("fused") implementation when
+        # the parameters live on the GPU (kwarg fused_optimizer=False restores the default one)
+        fused = bool(self.kwargs.get("fused_optimizer", True)) and all(p.is_cuda for p in params)
+        optimizer = torch.optim.SGD(params, lr=5e-5, momentum=self.kwargs.get("momentum"),
+                                    weight_decay=self.kwargs.get("weight_decay"), **({"fused": True} if fused else {}))
         return optimizer, None      # the reference builds a scheduler and discards it (:452-455)
 
     def segment(self, img, sync=True):

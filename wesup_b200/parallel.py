@@ -55,8 +55,16 @@ class GradientAllReduce:
         offset = 0
         for p in self.params:
             n = p.numel()
-            p.grad = self.flat[offset:offset + n].view_as(p)
+            p.grad = self._view(p, offset)
             offset += n
+
+    def _view(self, p, offset):
+        """The parameter's slot of the flat buffer, with the parameter's own strides (channels_last
+        convolution weights keep matching gradient strides, so the optimizer's multi-tensor path applies)."""
+        dense = p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last) if p.dim() == 4 else p.is_contiguous()
+        if dense:
+            return torch.as_strided(self.flat, p.size(), p.stride(), offset)
+        return self.flat[offset:offset + p.numel()].view_as(p)
 
     def zero_grad(self):
         """Use instead of optimizer.zero_grad(set_to_none=True), which would drop the views."""
@@ -66,7 +74,7 @@ class GradientAllReduce:
         offset = 0
         for p in self.params:
             n = p.numel()
-            view = self.flat[offset:offset + n].view_as(p)
+            view = self._view(p, offset)
             if p.grad is None:
                 view.zero_()
                 p.grad = view
