@@ -26,6 +26,7 @@
 // (fixed-point weight sums in shared memory), so results are bit-reproducible run to run.
 #include "common.cuh"
 #include <limits.h>
+#include <math.h>
 
 namespace wesup {
 
@@ -43,6 +44,7 @@ struct Groups {
     float sy[WESUP_MAX_LEVELS], sx[WESUP_MAX_LEVELS];
     int coff[WESUP_MAX_LEVELS], Cg[WESUP_MAX_LEVELS];
     int ident[WESUP_MAX_LEVELS];
+    float fscale[WESUP_MAX_LEVELS], finv[WESUP_MAX_LEVELS];   // fwd: 2^F and 2^-F of the fixed-point weight sums (0: no grid)
 };
 
 __device__ __forceinline__ void locate_level(const Levels &L, int l0, int l1, int c, int &l, int &cl) {
@@ -55,24 +57,29 @@ __device__ __forceinline__ void locate_level(const Levels &L, int l0, int l1, in
 // forward: one block per superpixel
 //
 // Weight aggregation: every pixel adds its 2x2 tap weights wy*wx to the cells of the
-// superpixel's low-res bounding box, held in shared memory as 64-bit FIXED-POINT sums
-// (32 fractional bits).  Integer adds commute, so the result does not depend on the
-// order in which the threads arrive: deterministic without a fixed summation order,
-// at a quantisation of 2^-33 per term (fp32 keeps 2^-24 of a weight of order 1).
-// The non-zero cells are then compacted into a list (cell offset, weight) and the
-// channel work streams over that list with independent 128-bit loads in flight.
+// superpixel's low-res bounding boxes (one per resolution group, side by side in shared
+// memory) as 32-bit FIXED-POINT sums -- native shared-memory integer atomics.  Integer
+// adds commute, so the result does not depend on the order in which threads arrive:
+// deterministic without a fixed summation order.  The number of fractional bits is chosen
+// per group so that the largest possible cell sum (the cell's footprint area) cannot
+// overflow: 27 bits at stride 2 ... 21 bits at stride 16 (fp32 itself keeps 24).
+// The non-zero cells are then compacted into per-group lists (cell offset, weight) and
+// the channel work streams over a list with independent 128-bit loads in flight.
 // ---------------------------------------------------------------------------
 struct CellW { int off; float w; };
+struct GInfo { int i_lo, j_lo, gw, cells, goff, lbeg, lend; };
 
 __global__ void __launch_bounds__(PF_THREADS) levels_pool_fwd_kernel(const Levels L, const Groups G,
                                                                      const int32_t *__restrict__ seg_offsets,
                                                                      const int32_t *__restrict__ seg_pixels,
                                                                      float *__restrict__ pooled) {
-    __shared__ unsigned long long grid[PF_GRID_CAP];
+    __shared__ unsigned grid[PF_GRID_CAP];
     __shared__ CellW cellw[PF_GRID_CAP];
     __shared__ float4 part[PF_THREADS];
+    __shared__ GInfo gi[WESUP_MAX_LEVELS];
     __shared__ int bbx[2];
-    __shared__ int warp_cnt[PF_THREADS / 32 + 1];
+    __shared__ int warp_cnt[PF_THREADS / 32];
+    __shared__ int total_cells;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int k = blockIdx.x;
     const int beg = __ldg(seg_offsets + k), end = __ldg(seg_offsets + k + 1);
@@ -98,67 +105,92 @@ __global__ void __launch_bounds__(PF_THREADS) levels_pool_fwd_kernel(const Level
         if (lane == 0) { atomicMin(&bbx[0], xmin); atomicMax(&bbx[1], xmax); }
     }
     __syncthreads();
-    const int ymin = __ldg(seg_pixels + beg) / W, ymax = __ldg(seg_pixels + end - 1) / W;
-    const int xmin = bbx[0], xmax = bbx[1];
+    if (tid == 0) {
+        const int ymin = __ldg(seg_pixels + beg) / W, ymax = __ldg(seg_pixels + end - 1) / W;
+        const int xmin = bbx[0], xmax = bbx[1];
+        int off = 0;
+        for (int g = 0; g < G.n; ++g) {
+            GInfo q;
+            q.i_lo = q.j_lo = 0; q.gw = 1; q.cells = 0; q.goff = off; q.lbeg = q.lend = 0;
+            if (!G.ident[g] && G.fscale[g] > 0.f) {
+                q.i_lo = bilinear_tap(ymin, G.sy[g], G.h[g]).i0;
+                q.j_lo = bilinear_tap(xmin, G.sx[g], G.w[g]).i0;
+                const long gh = bilinear_tap(ymax, G.sy[g], G.h[g]).i1 - q.i_lo + 1;
+                q.gw = bilinear_tap(xmax, G.sx[g], G.w[g]).i1 - q.j_lo + 1;
+                if (off + gh * q.gw <= PF_GRID_CAP) { q.cells = (int)gh * q.gw; off += q.cells; }
+            }
+            gi[g] = q;
+        }
+        total_cells = off;
+    }
+    __syncthreads();
+    const int total = total_cells;
+    for (int e = tid; e < total; e += PF_THREADS) grid[e] = 0u;
+    __syncthreads();
+    for (int it = beg + tid; it < end; it += PF_THREADS) {
+        const int p = __ldg(seg_pixels + it);
+        const int y = p / W, x = p - y * W;
+        for (int g = 0; g < G.n; ++g) {
+            const GInfo q = gi[g];
+            if (q.cells == 0) continue;
+            const Tap ty = bilinear_tap(y, G.sy[g], G.h[g]), tx = bilinear_tap(x, G.sx[g], G.w[g]);
+            unsigned *gp = grid + q.goff;
+            const int r0 = (ty.i0 - q.i_lo) * q.gw, r1 = (ty.i1 - q.i_lo) * q.gw, c0 = tx.i0 - q.j_lo, c1 = tx.i1 - q.j_lo;
+            const float fs = G.fscale[g];
+            const float a0 = ty.w0 * fs, a1 = ty.w1 * fs;            // exact: fs is a power of two
+            atomicAdd(gp + r0 + c0, __float2uint_rn(a0 * tx.w0));
+            atomicAdd(gp + r0 + c1, __float2uint_rn(a0 * tx.w1));
+            atomicAdd(gp + r1 + c0, __float2uint_rn(a1 * tx.w0));
+            atomicAdd(gp + r1 + c1, __float2uint_rn(a1 * tx.w1));
+        }
+    }
+    __syncthreads();
+    // compact the non-zero cells, group after group (order: cell index -- fixed)
+    int n_list = 0;
+    for (int e0 = 0; e0 < total; e0 += PF_THREADS) {
+        const int e = e0 + tid;
+        const unsigned v = e < total ? grid[e] : 0u;
+        const unsigned m = __ballot_sync(0xffffffffu, v != 0u);
+        if (lane == 0) warp_cnt[wid] = __popc(m);
+        __syncthreads();
+        int before = n_list, tot = n_list;
+#pragma unroll
+        for (int q = 0; q < PF_THREADS / 32; ++q) {
+            const int c = warp_cnt[q];
+            if (q < wid) before += c;
+            tot += c;
+        }
+        if (e < total) {
+            int g = 0;
+            while (e >= gi[g].goff + gi[g].cells) ++g;
+            const int pos = before + __popc(m & ((1u << lane) - 1u));
+            const int local = e - gi[g].goff, gw = gi[g].gw;
+            if (local == 0) gi[g].lbeg = pos;
+            if (v != 0u) {
+                const int i = __float2int_rd(((float)local + 0.5f) / (float)gw), j = local - i * gw;
+                CellW cw;
+                cw.off = i * G.w[g] + j;
+                cw.w = (float)v * G.finv[g];
+                cellw[pos] = cw;
+            }
+        }
+        n_list = tot;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int nxt = n_list;
+        for (int g = G.n - 1; g >= 0; --g)
+            if (gi[g].cells > 0) { gi[g].lend = nxt; nxt = gi[g].lbeg; }
+    }
+    __syncthreads();
     const float inv = 1.0f / (float)n;
 
     for (int g = 0; g < G.n; ++g) {
         const int nch4 = G.Cg[g] >> 2;
         const int hl = G.h[g], wl = G.w[g];
-        const float sy = G.sy[g], sx = G.sx[g];
         const bool ident = G.ident[g] != 0;
-        int i_lo = 0, j_lo = 0, gw = 1, cells = 0, n_list = 0;
-        bool use_grid = false;
-        if (!ident) {
-            i_lo = bilinear_tap(ymin, sy, hl).i0;
-            j_lo = bilinear_tap(xmin, sx, wl).i0;
-            const int gh = bilinear_tap(ymax, sy, hl).i1 - i_lo + 1;
-            gw = bilinear_tap(xmax, sx, wl).i1 - j_lo + 1;
-            use_grid = (long)gh * gw <= PF_GRID_CAP;
-            cells = use_grid ? gh * gw : 0;
-        }
-        if (use_grid) {
-            for (int e = tid; e < cells; e += PF_THREADS) grid[e] = 0ull;
-            __syncthreads();
-            for (int it = beg + tid; it < end; it += PF_THREADS) {
-                const int p = __ldg(seg_pixels + it);
-                const int y = p / W, x = p - y * W;
-                const Tap ty = bilinear_tap(y, sy, hl), tx = bilinear_tap(x, sx, wl);
-                const int r0 = (ty.i0 - i_lo) * gw, r1 = (ty.i1 - i_lo) * gw, c0 = tx.i0 - j_lo, c1 = tx.i1 - j_lo;
-                // 2^32 * w rounded to nearest; w in [0, 1]
-                atomicAdd(&grid[r0 + c0], (unsigned long long)__float2ll_rn(ty.w0 * tx.w0 * 4294967296.0f));
-                atomicAdd(&grid[r0 + c1], (unsigned long long)__float2ll_rn(ty.w0 * tx.w1 * 4294967296.0f));
-                atomicAdd(&grid[r1 + c0], (unsigned long long)__float2ll_rn(ty.w1 * tx.w0 * 4294967296.0f));
-                atomicAdd(&grid[r1 + c1], (unsigned long long)__float2ll_rn(ty.w1 * tx.w1 * 4294967296.0f));
-            }
-            __syncthreads();
-            // compact the non-zero cells (order: round, warp, lane -- fixed)
-            const float inv_gw = 1.0f / (float)gw;
-            int base_pos = 0;
-            for (int e0 = 0; e0 < cells; e0 += PF_THREADS) {
-                const int e = e0 + tid;
-                const unsigned long long v = e < cells ? grid[e] : 0ull;
-                const unsigned m = __ballot_sync(0xffffffffu, v != 0ull);
-                if (lane == 0) warp_cnt[wid] = __popc(m);
-                __syncthreads();
-                int before = base_pos, total = base_pos;
-                for (int q = 0; q < PF_THREADS / 32; ++q) {
-                    const int c = warp_cnt[q];
-                    if (q < wid) before += c;
-                    total += c;
-                }
-                if (v != 0ull) {
-                    const int i = __float2int_rd(((float)e + 0.5f) * inv_gw), j = e - i * gw;
-                    CellW cw;
-                    cw.off = i * wl + j;
-                    cw.w = (float)((double)v * (1.0 / 4294967296.0));
-                    cellw[before + __popc(m & ((1u << lane) - 1u))] = cw;
-                }
-                base_pos = total;
-                __syncthreads();
-            }
-            n_list = base_pos;
-        }
+        const GInfo q = gi[g];
+        const bool use_grid = q.cells > 0;
         // ---- channel work: thread = (slice of the items, 4-channel group) ----------------
         for (int cb = 0; cb < nch4; cb += PF_THREADS) {
             const int active = min(nch4 - cb, PF_THREADS);
@@ -185,9 +217,9 @@ __global__ void __launch_bounds__(PF_THREADS) levels_pool_fwd_kernel(const Level
                     }
                     for (; it < end; it += nsl) acc = acc + __ldg(reinterpret_cast<const float4 *>(src + (long)__ldg(seg_pixels + it) * Cl));
                 } else if (use_grid) {
-                    const float *__restrict__ base = src + ((long)i_lo * wl + j_lo) * Cl;
-                    int e = sl;
-                    for (; e + 3 * nsl < n_list; e += 4 * nsl) {
+                    const float *__restrict__ base = src + ((long)q.i_lo * wl + q.j_lo) * Cl;
+                    int e = q.lbeg + sl;
+                    for (; e + 3 * nsl < q.lend; e += 4 * nsl) {
                         const CellW a0 = cellw[e], a1 = cellw[e + nsl], a2 = cellw[e + 2 * nsl], a3 = cellw[e + 3 * nsl];
                         const float4 v0 = __ldg(reinterpret_cast<const float4 *>(base + (long)a0.off * Cl));
                         const float4 v1 = __ldg(reinterpret_cast<const float4 *>(base + (long)a1.off * Cl));
@@ -195,12 +227,13 @@ __global__ void __launch_bounds__(PF_THREADS) levels_pool_fwd_kernel(const Level
                         const float4 v3 = __ldg(reinterpret_cast<const float4 *>(base + (long)a3.off * Cl));
                         fma4(acc, a0.w, v0); fma4(acc, a1.w, v1); fma4(acc, a2.w, v2); fma4(acc, a3.w, v3);
                     }
-                    for (; e < n_list; e += nsl) {
+                    for (; e < q.lend; e += nsl) {
                         const CellW a0 = cellw[e];
                         fma4(acc, a0.w, __ldg(reinterpret_cast<const float4 *>(base + (long)a0.off * Cl)));
                     }
                 } else {
                     // bounding box too large for the shared grid (huge / scattered superpixel): per-pixel taps
+                    const float sy = G.sy[g], sx = G.sx[g];
                     for (int it = beg + sl; it < end; it += nsl) {
                         const int p = __ldg(seg_pixels + it);
                         const int y = p / W, x = p - y * W;
@@ -219,13 +252,12 @@ __global__ void __launch_bounds__(PF_THREADS) levels_pool_fwd_kernel(const Level
                 part[tid] = acc;
                 __syncthreads();
                 if (sl == 0) {
-                    for (int s = 1; s < nsl; ++s) acc = acc + part[s * active + tid];
+                    for (int s_ = 1; s_ < nsl; ++s_) acc = acc + part[s_ * active + tid];
                 }
             }
             if (live && sl == 0) *reinterpret_cast<float4 *>(out + G.coff[g] + (c4 << 2)) = inv * acc;
             if (nsl > 1) __syncthreads();
         }
-        __syncthreads();       // grid[] / cellw[] are rewritten by the next group
     }
 }
 
@@ -238,6 +270,7 @@ __global__ void __launch_bounds__(PF_THREADS) levels_pool_fwd_kernel(const Level
 // its channel groups of that pooled-gradient row.
 // ---------------------------------------------------------------------------
 struct Staged { int lab; float w; };
+constexpr int PB_LIST = 64;          // distinct superpixels of one cell collected before their rows are gathered
 
 __device__ __forceinline__ void footprint_range(int i, float scale, int out_size, int &lo, int &hi) {
     if (!(scale > 0.f)) { lo = 0; hi = out_size - 1; return; }
@@ -253,79 +286,102 @@ __global__ void __launch_bounds__(PB_WARPS * 32) levels_pool_bwd_kernel(const Le
                                                                         const float *__restrict__ gp,
                                                                         const int32_t *__restrict__ row_labels,
                                                                         const int32_t *__restrict__ counts) {
-    extern __shared__ Staged stage_all[];
+    extern __shared__ Staged smem_bwd[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int hg = G.h[g], wg = G.w[g];
     const long q = (long)blockIdx.x * PB_WARPS + wid;
     if (q >= (long)hg * wg) return;
     const int nch4 = G.Cg[g] >> 2, Ctot = L.Ctot, W = L.W;
     const float *__restrict__ gpg = gp + G.coff[g];
+    Staged *st = smem_bwd + (long)wid * stage_cap;
+    Staged *list = smem_bwd + (long)PB_WARPS * stage_cap + wid * PB_LIST;
     float4 acc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (G.ident[g]) {
-        const int k = __ldg(row_labels + q);
-        if (k >= 0) {
-            const int cnt = __ldg(counts + k);
-            const float wv = cnt > 0 ? 1.0f / (float)cnt : 0.f;
-            const float *__restrict__ row = gpg + (long)k * Ctot;
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const int c4 = lane + 32 * v;
-                if (c4 < nch4) acc[v] = wv * __ldg(reinterpret_cast<const float4 *>(row) + c4);
-            }
-        }
-    } else {
-        const int i = (int)(q / wg), j = (int)(q - (long)i * wg);
-        const float sy = G.sy[g], sx = G.sx[g];
-        int ylo, yhi, xlo, xhi;
-        footprint_range(i, sy, L.H, ylo, yhi);
-        footprint_range(j, sx, W, xlo, xhi);
-        const int nx = xhi - xlo + 1, nf = (yhi - ylo + 1) * nx;
-        const float inv_nx = 1.0f / (float)nx;
-        Staged *st = stage_all + (long)wid * stage_cap;
-        const bool staged = nf <= stage_cap;
-        auto fetch = [&](int t) {
-            const int a = __float2int_rd(((float)t + 0.5f) * inv_nx), b = t - a * nx;
-            const int y = ylo + a, x = xlo + b;
-            const Tap ty = bilinear_tap(y, sy, hg), tx = bilinear_tap(x, sx, wg);
-            const float wy = (ty.i0 == i ? ty.w0 : 0.f) + (ty.i1 == i ? ty.w1 : 0.f);
-            const float wx = (tx.i0 == j ? tx.w0 : 0.f) + (tx.i1 == j ? tx.w1 : 0.f);
-            Staged s;
-            s.w = wy * wx;
-            s.lab = (s.w != 0.f) ? __ldg(row_labels + (long)y * W + x) : -1;
-            return s;
-        };
-        int cur = INT_MAX;
-        for (int t = lane; t < nf; t += 32) {
-            const Staged s = fetch(t);
-            if (staged) st[t] = s;
-            if (s.lab >= 0) cur = min(cur, s.lab);
+    const int i = (int)(q / wg), j = (int)(q - (long)i * wg);
+    const float sy = G.sy[g], sx = G.sx[g];
+    int ylo, yhi, xlo, xhi;
+    footprint_range(i, sy, L.H, ylo, yhi);
+    footprint_range(j, sx, W, xlo, xhi);
+    const int nx = xhi - xlo + 1, nf = (yhi - ylo + 1) * nx;
+    const float inv_nx = 1.0f / (float)nx;
+    const bool staged = nf <= stage_cap;
+    auto fetch = [&](int t) {
+        const int a = __float2int_rd(((float)t + 0.5f) * inv_nx), b = t - a * nx;
+        const int y = ylo + a, x = xlo + b;
+        const Tap ty = bilinear_tap(y, sy, hg), tx = bilinear_tap(x, sx, wg);
+        const float wy = (ty.i0 == i ? ty.w0 : 0.f) + (ty.i1 == i ? ty.w1 : 0.f);
+        const float wx = (tx.i0 == j ? tx.w0 : 0.f) + (tx.i1 == j ? tx.w1 : 0.f);
+        Staged s;
+        s.w = wy * wx;
+        s.lab = (s.w != 0.f) ? __ldg(row_labels + (long)y * W + x) : -1;
+        return s;
+    };
+    // gather the rows of the collected superpixels: all loads of an entry are independent
+    auto flush = [&](int nl) {
+        __syncwarp();
+        for (int e = lane; e < nl; e += 32) {
+            const int cnt = __ldg(counts + list[e].lab);
+            list[e].w = cnt > 0 ? list[e].w / (float)cnt : 0.f;
         }
         __syncwarp();
-        cur = __reduce_min_sync(0xffffffffu, cur);
-        while (cur != INT_MAX) {
-            float ws = 0.f;
-            int nxt = INT_MAX;
-            for (int t = lane; t < nf; t += 32) {
-                const Staged s = staged ? st[t] : fetch(t);
-                if (s.lab == cur) ws += s.w;
-                else if (s.lab > cur) nxt = min(nxt, s.lab);
+        constexpr int U = V >= 6 ? 1 : (V >= 4 ? 2 : 4);
+        int e = 0;
+        for (; e + U <= nl; e += U) {
+            float4 val[U][V];
+            float wv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const Staged en = list[e + u];
+                wv[u] = en.w;
+                const float4 *__restrict__ row = reinterpret_cast<const float4 *>(gpg + (long)en.lab * Ctot);
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const int c4 = lane + 32 * v;
+                    val[u][v] = c4 < nch4 ? __ldg(row + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
-            nxt = __reduce_min_sync(0xffffffffu, nxt);
-            const int cnt = __ldg(counts + cur);
-            ws = cnt > 0 ? ws / (float)cnt : 0.f;
-            const float *__restrict__ row = gpg + (long)cur * Ctot;
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int v = 0; v < V; ++v) fma4(acc[v], wv[u], val[u][v]);
+        }
+        for (; e < nl; ++e) {
+            const Staged en = list[e];
+            const float4 *__restrict__ row = reinterpret_cast<const float4 *>(gpg + (long)en.lab * Ctot);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 const int c4 = lane + 32 * v;
-                if (c4 < nch4) fma4(acc[v], ws, __ldg(reinterpret_cast<const float4 *>(row) + c4));
+                if (c4 < nch4) fma4(acc[v], en.w, __ldg(row + c4));
             }
-            cur = nxt;
         }
+        __syncwarp();
+    };
+    int cur = INT_MAX;
+    for (int t = lane; t < nf; t += 32) {
+        const Staged s = fetch(t);
+        if (staged) st[t] = s;
+        if (s.lab >= 0) cur = min(cur, s.lab);
     }
+    __syncwarp();
+    cur = __reduce_min_sync(0xffffffffu, cur);
+    int nl = 0;
+    while (cur != INT_MAX) {
+        float ws = 0.f;
+        int nxt = INT_MAX;
+        for (int t = lane; t < nf; t += 32) {
+            const Staged s = staged ? st[t] : fetch(t);
+            if (s.lab == cur) ws += s.w;
+            else if (s.lab > cur) nxt = min(nxt, s.lab);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
+        nxt = __reduce_min_sync(0xffffffffu, nxt);
+        if (lane == 0) { list[nl].lab = cur; list[nl].w = ws; }
+        if (++nl == PB_LIST) { flush(nl); nl = 0; }
+        cur = nxt;
+    }
+    flush(nl);
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         const int c4 = lane + 32 * v;
@@ -333,6 +389,46 @@ __global__ void __launch_bounds__(PB_WARPS * 32) levels_pool_bwd_kernel(const Le
             int l, cl;
             locate_level(L, G.l0[g], G.l1[g], c4 << 2, l, cl);
             *reinterpret_cast<float4 *>(L.dst[l] + q * L.C[l] + cl) = acc[v];
+        }
+    }
+}
+
+// full-resolution levels: grad[p, c] = grad_pooled[row(p), c] / |S_row(p)|; four pixels per thread so
+// that the label -> count -> row chain of four pixels is in flight together
+__global__ void __launch_bounds__(256) levels_pool_bwd_ident_kernel(const Levels L, const Groups G, int g,
+                                                                    const float *__restrict__ gp,
+                                                                    const int32_t *__restrict__ row_labels,
+                                                                    const int32_t *__restrict__ counts, long HW) {
+    const int nch4 = G.Cg[g] >> 2, Ctot = L.Ctot;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long quad = idx / nch4;
+    const int c4 = (int)(idx - quad * nch4);
+    const long p0 = quad * 4;
+    if (p0 >= HW) return;
+    int lab[4];
+    if (p0 + 3 < HW && (reinterpret_cast<uintptr_t>(row_labels) & 15u) == 0) {
+        const int4 t = __ldg(reinterpret_cast<const int4 *>(row_labels + p0));
+        lab[0] = t.x; lab[1] = t.y; lab[2] = t.z; lab[3] = t.w;
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) lab[u] = p0 + u < HW ? __ldg(row_labels + p0 + u) : -1;
+    }
+    int cnt[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cnt[u] = lab[u] >= 0 ? __ldg(counts + lab[u]) : 0;
+    float4 val[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        val[u] = lab[u] >= 0 ? __ldg(reinterpret_cast<const float4 *>(gp + G.coff[g] + (long)lab[u] * Ctot) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int l, cl;
+    locate_level(L, G.l0[g], G.l1[g], c4 << 2, l, cl);
+    float *__restrict__ dst = L.dst[l] + cl;
+    const int Cl = L.C[l];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (p0 + u < HW) {
+            const float wv = cnt[u] > 0 ? 1.0f / (float)cnt[u] : 0.f;
+            *reinterpret_cast<float4 *>(dst + (p0 + u) * Cl) = wv * val[u];
         }
     }
 }
@@ -355,6 +451,12 @@ static int build_groups(Groups &G, const Levels &L) {
             G.sy[n] = L.sy[l]; G.sx[n] = L.sx[l];
             G.coff[n] = L.coff[l]; G.Cg[n] = L.C[l];
             G.ident[n] = (L.h[l] == L.H && L.w[l] == L.W) ? 1 : 0;
+            // fixed-point format of the forward's weight sums: a cell's sum is at most its footprint area
+            const double fy = L.sy[l] > 0.f ? 2.0 / L.sy[l] + 2.0 : (double)L.H;
+            const double fx = L.sx[l] > 0.f ? 2.0 / L.sx[l] + 2.0 : (double)L.W;
+            const int bits = 31 - (int)ceil(log2(fy * fx + 1.0));
+            G.fscale[n] = bits >= 16 ? (float)ldexp(1.0, bits) : 0.f;
+            G.finv[n] = bits >= 16 ? (float)ldexp(1.0, -bits) : 0.f;
         }
     }
     return 0;
@@ -387,7 +489,7 @@ static inline int stage_need(float scale, int out_size) {
 template <int V>
 static void launch_bwd(const Levels &L, const Groups &G, int g, int stage_cap, const float *gp, const int32_t *row_labels,
                        const int32_t *counts, cudaStream_t stream) {
-    const size_t smem = (size_t)PB_WARPS * stage_cap * sizeof(Staged);
+    const size_t smem = (size_t)PB_WARPS * (stage_cap + PB_LIST) * sizeof(Staged);
     if (smem > 48 * 1024) cudaFuncSetAttribute(levels_pool_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const long cells = (long)G.h[g] * G.w[g];
     levels_pool_bwd_kernel<V><<<cdiv(cells, PB_WARPS), PB_WARPS * 32, smem, stream>>>(L, G, g, stage_cap, gp, row_labels, counts);
@@ -434,18 +536,21 @@ extern "C" int wesup_levels_pool_bwd(const float *grad_pooled, const int32_t *ro
     // coarse groups first: their warps carry the longest footprint walks
     int launched = 0;
     for (int g = G.n - 1; g >= 0; --g) {
-        int stage_cap = 1;
-        if (!G.ident[g]) {
-            const long need = (long)stage_need(G.sy[g], H) * stage_need(G.sx[g], W);
-            stage_cap = (int)(need < PB_STAGE_MAX ? need : PB_STAGE_MAX);
+        ++launched;
+        if (G.ident[g]) {
+            const long HW = (long)H * W;
+            const long items = ((HW + 3) / 4) * (G.Cg[g] / 4);
+            levels_pool_bwd_ident_kernel<<<cdiv(items, 256), 256, 0, stream>>>(L, G, g, grad_pooled, row_labels, counts, HW);
+            continue;
         }
+        const long need = (long)stage_need(G.sy[g], H) * stage_need(G.sx[g], W);
+        const int stage_cap = (int)(need < PB_STAGE_MAX ? need : PB_STAGE_MAX);
         const int v = (G.Cg[g] / 4 + 31) / 32;
         if (v <= 1) launch_bwd<1>(L, G, g, stage_cap, grad_pooled, row_labels, counts, stream);
         else if (v <= 2) launch_bwd<2>(L, G, g, stage_cap, grad_pooled, row_labels, counts, stream);
         else if (v <= 4) launch_bwd<4>(L, G, g, stage_cap, grad_pooled, row_labels, counts, stream);
         else if (v <= 6) launch_bwd<6>(L, G, g, stage_cap, grad_pooled, row_labels, counts, stream);
         else launch_bwd<PB_VMAX>(L, G, g, stage_cap, grad_pooled, row_labels, counts, stream);
-        ++launched;
     }
     WESUP_CHECK_LAUNCH("wesup_levels_pool_bwd", launched);
     return 0;

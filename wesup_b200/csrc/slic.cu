@@ -168,19 +168,19 @@ __global__ void slic_init_kernel(SlicWs s, long K, int nx, int step, int start, 
 constexpr int AT = 16;              // tile edge
 constexpr int MAX_CAND = 192;       // candidate centres kept in shared memory per tile
 
-struct Cand {
-    double cy, cx, l, a, b;
-    int k, y0, y1, x0, x1;
+// candidates of a tile, structure-of-arrays; "near" centres (inside the tile grown by half a
+// grid step) fill the list from the front, the others from the back, so that every pixel meets
+// its likely winners first and the spatial lower bound prunes most of the rest
+struct Cands {
+    double cy[MAX_CAND], cx[MAX_CAND], l[MAX_CAND], a[MAX_CAND], b[MAX_CAND];
+    int k[MAX_CAND];
+    unsigned ywin[MAX_CAND], xwin[MAX_CAND];     // lo | hi << 16 of the centre's clipped 2S window
 };
 
 __global__ void __launch_bounds__(256, 6) slic_sweep_kernel(SlicWs s, int H, int W, long K, int step, double spatial_weight) {
-    __shared__ Cand cand[MAX_CAND];
-    __shared__ double px_lab[3][256];
-    __shared__ short px_slot[256];
-    __shared__ unsigned used_bits[MAX_CAND / 32];
-    __shared__ short used_list[MAX_CAND];
-    __shared__ int n_cand_s, n_used_s, is_last;
-    const int tid = threadIdx.x;
+    __shared__ Cands cand;
+    __shared__ int n_near_s, n_far_s, is_last;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int tx0 = blockIdx.x * AT, ty0 = blockIdx.y * AT;
     const int x = tx0 + (tid & (AT - 1)), y = ty0 + (tid >> 4);
     const bool live = x < W && y < H;
@@ -188,29 +188,32 @@ __global__ void __launch_bounds__(256, 6) slic_sweep_kernel(SlicWs s, int H, int
     const long p = (long)y * W + x;
     double pl = 0, pa = 0, pb = 0;
     if (live) { pl = s.lab[p]; pa = s.lab[HW + p]; pb = s.lab[2 * HW + p]; }
-    if (tid == 0) { n_cand_s = 0; n_used_s = 0; }
-    if (tid < MAX_CAND / 32) used_bits[tid] = 0u;
+    if (tid == 0) { n_near_s = 0; n_far_s = 0; }
     __syncthreads();
     // ---- gather the centres whose 2S window intersects this tile -------------
     const double two_s = (double)(2 * step);
-    auto consider = [&](int k) {
-        const double cy = s.cent[5 * k], cx = s.cent[5 * k + 1];
-        double lo;
-        lo = cy - two_s;       const int y0 = (int)(lo > 0.0 ? lo : 0.0);
-        lo = cy + two_s + 1.0; const int y1 = (int)(lo < (double)H ? lo : (double)H);
-        lo = cx - two_s;       const int x0 = (int)(lo > 0.0 ? lo : 0.0);
-        lo = cx + two_s + 1.0; const int x1 = (int)(lo < (double)W ? lo : (double)W);
-        if (y0 < ty0 + AT && y1 > ty0 && x0 < tx0 + AT && x1 > tx0) {
-            const int slot = atomicAdd(&n_cand_s, 1);
-            if (slot < MAX_CAND) {
-                Cand c;
-                c.cy = cy; c.cx = cx; c.l = s.cent[5 * k + 2]; c.a = s.cent[5 * k + 3]; c.b = s.cent[5 * k + 4];
-                c.k = k; c.y0 = y0; c.y1 = y1; c.x0 = x0; c.x1 = x1;
-                cand[slot] = c;
-            }
-        }
-    };
     {
+        const double half = (double)(step / 2 + 1);
+        const double ny0 = (double)ty0 - half, ny1 = (double)(ty0 + AT) + half, nx0 = (double)tx0 - half, nx1 = (double)(tx0 + AT) + half;
+        auto consider = [&](int k) {
+            const double cy = s.cent[5 * k], cx = s.cent[5 * k + 1];
+            double lo;
+            lo = cy - two_s;       const int y0 = (int)(lo > 0.0 ? lo : 0.0);
+            lo = cy + two_s + 1.0; const int y1 = (int)(lo < (double)H ? lo : (double)H);
+            lo = cx - two_s;       const int x0 = (int)(lo > 0.0 ? lo : 0.0);
+            lo = cx + two_s + 1.0; const int x1 = (int)(lo < (double)W ? lo : (double)W);
+            if (y0 < ty0 + AT && y1 > ty0 && x0 < tx0 + AT && x1 > tx0) {
+                const bool near = cy >= ny0 && cy < ny1 && cx >= nx0 && cx < nx1;
+                const int slot = near ? atomicAdd(&n_near_s, 1) : MAX_CAND - 1 - atomicAdd(&n_far_s, 1);
+                if (slot >= 0 && slot < MAX_CAND) {       // on overflow the list is abandoned (exhaustive scan below)
+                    cand.cy[slot] = cy; cand.cx[slot] = cx;
+                    cand.l[slot] = s.cent[5 * k + 2]; cand.a[slot] = s.cent[5 * k + 3]; cand.b[slot] = s.cent[5 * k + 4];
+                    cand.k[slot] = k;
+                    cand.ywin[slot] = (unsigned)y0 | ((unsigned)y1 << 16);
+                    cand.xwin[slot] = (unsigned)x0 | ((unsigned)x1 << 16);
+                }
+            }
+        };
         // a centre can reach the tile only from cells within 2S+1 pixels of it
         const int reach = 2 * step + 1;
         const int by0 = max((ty0 - reach) / step - 1, 0), by1 = min((ty0 + AT - 1 + reach) / step, s.cells_y - 1);
@@ -225,28 +228,34 @@ __global__ void __launch_bounds__(256, 6) slic_sweep_kernel(SlicWs s, int H, int
         for (int i = tid; i < n_ov; i += 256) consider(s.ov_items[i]);
     }
     __syncthreads();
-    const int n_total = n_cand_s;
-    const int n = min(n_total, MAX_CAND);
+    const int n_near = n_near_s, n_far = n_far_s;
+    const bool overflow = n_near + n_far > MAX_CAND;
     double best = CUDART_INF;
-    int best_k = -1, best_slot = -1;
-    if (live) {
-        for (int i = 0; i < n; ++i) {
-            const Cand &c = cand[i];
-            if (y < c.y0 || y >= c.y1 || x < c.x0 || x >= c.x1) continue;
-            double dy = __dadd_rn(c.cy, -(double)y); dy = __dmul_rn(dy, dy);
-            double dx = __dadd_rn(c.cx, -(double)x); dx = __dmul_rn(dx, dx);
-            double d = __dmul_rn(__dadd_rn(dy, dx), spatial_weight);
-            double t = __dadd_rn(pl, -c.l);
-            double dc = __dmul_rn(t, t);                       // 0 + t*t
-            t = __dadd_rn(pa, -c.a); dc = __dadd_rn(dc, __dmul_rn(t, t));
-            t = __dadd_rn(pb, -c.b); dc = __dadd_rn(dc, __dmul_rn(t, t));
-            d = __dadd_rn(d, dc);
-            if (d < best || (d == best && c.k < best_k)) { best = d; best_k = c.k; best_slot = i; }
-        }
+    int best_k = -1;
+    auto evaluate = [&](int i) {
+        const unsigned yw = cand.ywin[i], xw = cand.xwin[i];
+        if (y < (int)(yw & 0xffffu) || y >= (int)(yw >> 16) || x < (int)(xw & 0xffffu) || x >= (int)(xw >> 16)) return;
+        double dy = __dadd_rn(cand.cy[i], -(double)y); dy = __dmul_rn(dy, dy);
+        double dx = __dadd_rn(cand.cx[i], -(double)x); dx = __dmul_rn(dx, dx);
+        double d = __dmul_rn(__dadd_rn(dy, dx), spatial_weight);
+        // d only grows when the (non-negative) colour term is added and rounding is monotone:
+        // a centre whose spatial term alone exceeds the best distance can neither win nor tie
+        if (d > best) return;
+        double t = __dadd_rn(pl, -cand.l[i]);
+        double dc = __dmul_rn(t, t);                       // 0 + t*t
+        t = __dadd_rn(pa, -cand.a[i]); dc = __dadd_rn(dc, __dmul_rn(t, t));
+        t = __dadd_rn(pb, -cand.b[i]); dc = __dadd_rn(dc, __dmul_rn(t, t));
+        d = __dadd_rn(d, dc);
+        const int k = cand.k[i];
+        if (d < best || (d == best && k < best_k)) { best = d; best_k = k; }
+    };
+    if (live && !overflow) {
+        for (int i = 0; i < n_near; ++i) evaluate(i);
+        for (int i = MAX_CAND - n_far; i < MAX_CAND; ++i) evaluate(i);
     }
-    if (n_total > MAX_CAND) {
-        // pathological crowding: the shared list overflowed; finish with the exhaustive scan
-        // over all centres (same arithmetic, same tie break) so the result stays exact
+    if (overflow) {
+        // pathological crowding: the shared list overflowed; exhaustive scan over all centres
+        // (same arithmetic, same tie break) so the result stays exact
         if (live) {
             for (long k = 0; k < K; ++k) {
                 const double cy = s.cent[5 * k], cx = s.cent[5 * k + 1];
@@ -265,72 +274,43 @@ __global__ void __launch_bounds__(256, 6) slic_sweep_kernel(SlicWs s, int H, int
                 t = __dadd_rn(pa, -s.cent[5 * k + 3]); dc = __dadd_rn(dc, __dmul_rn(t, t));
                 t = __dadd_rn(pb, -s.cent[5 * k + 4]); dc = __dadd_rn(dc, __dmul_rn(t, t));
                 d = __dadd_rn(d, dc);
-                if (d < best || (d == best && (int)k < best_k)) { best = d; best_k = (int)k; best_slot = -1; }
+                if (d < best || (d == best && (int)k < best_k)) { best = d; best_k = (int)k; }
             }
         }
     }
     // ---- accumulate the new cluster sums ---------------------------------------
-    // Per-tile pre-aggregation without shared-memory fp64 atomics (a CAS loop under
-    // ~40-way contention): pixels publish (slot, L, a, b); thread t then owns candidate
-    // slot t>>2 and a quarter t&3 of the tile, sums its matches in pixel order, the four
-    // quarters meet in a fixed-order shuffle tree, and one thread per touched cluster
-    // issues the global atomics (~9 clusters per tile instead of 256 pixels x 6).
-    int k_final = best_k;
+    // Warp-level pre-aggregation (a warp is a 16x2 strip of the tile and meets 1-4 clusters):
+    // the lanes of one cluster are reduced together -- integer sums with redux, colour sums with
+    // a fixed butterfly -- and one lane issues the six global atomics.  No block barrier.
+    int kf = -1;
     if (live) {
-        if (k_final >= 0) s.nearest[p] = k_final; else { k_final = s.nearest[p]; best_slot = -1; }   // uncovered pixel keeps its previous cluster
-        if (best_slot < 0) {                              // rare: not in the shared list -> straight to global
-            atomicAdd(&s.acc_n[3 * k_final], 1ull);
-            atomicAdd(&s.acc_n[3 * k_final + 1], (u64)y);
-            atomicAdd(&s.acc_n[3 * k_final + 2], (u64)x);
-            atomicAdd(&s.acc_c[3 * k_final], pl);
-            atomicAdd(&s.acc_c[3 * k_final + 1], pa);
-            atomicAdd(&s.acc_c[3 * k_final + 2], pb);
-        }
+        kf = best_k;
+        if (kf >= 0) s.nearest[p] = kf; else kf = s.nearest[p];      // uncovered pixel keeps its previous cluster
     }
-    px_slot[tid] = (live && best_slot >= 0) ? (short)best_slot : (short)-1;
-    px_lab[0][tid] = pl; px_lab[1][tid] = pa; px_lab[2][tid] = pb;
-    if (live && best_slot >= 0) atomicOr(&used_bits[best_slot >> 5], 1u << (best_slot & 31));
-    __syncthreads();
-    if (tid < n && ((used_bits[tid >> 5] >> (tid & 31)) & 1u)) {     // dense list of the slots that own pixels (ascending)
-        int pos = __popc(used_bits[tid >> 5] & ((1u << (tid & 31)) - 1u));
-        for (int wd = 0; wd < (tid >> 5); ++wd) pos += __popc(used_bits[wd]);
-        used_list[pos] = (short)tid;
-        atomicAdd(&n_used_s, 1);
-    }
-    __syncthreads();
-    const int n_used = n_used_s;
-    for (int base = 0; base < n_used; base += 64) {
-        const int ui = base + (tid >> 2), q = tid & 3;
-        const int slot = ui < n_used ? (int)used_list[ui] : n;
-        unsigned cnt = 0, sy = 0, sx = 0;
-        double sl = 0.0, sa = 0.0, sb = 0.0;
-        if (slot < n) {
-            for (int i = q * 64; i < q * 64 + 64; ++i) {
-                if (px_slot[i] == slot) {
-                    ++cnt; sy += (unsigned)(ty0 + (i >> 4)); sx += (unsigned)(tx0 + (i & (AT - 1)));
-                    sl += px_lab[0][i]; sa += px_lab[1][i]; sb += px_lab[2][i];
-                }
-            }
-        }
+    unsigned todo = __ballot_sync(0xffffffffu, kf >= 0);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int key = __shfl_sync(0xffffffffu, kf, leader);
+        const bool mine = kf == key;
+        const unsigned grp = __ballot_sync(0xffffffffu, mine);
+        const unsigned sy = __reduce_add_sync(0xffffffffu, mine ? (unsigned)y : 0u);
+        const unsigned sx = __reduce_add_sync(0xffffffffu, mine ? (unsigned)x : 0u);
+        double sl = mine ? pl : 0.0, sa = mine ? pa : 0.0, sb = mine ? pb : 0.0;
 #pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
-            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-            sy += __shfl_xor_sync(0xffffffffu, sy, o);
-            sx += __shfl_xor_sync(0xffffffffu, sx, o);
-            // fixed pairing (q^1 then q^2): every lane of the quad ends with the same bits
-            const double tl = __shfl_xor_sync(0xffffffffu, sl, o), ta = __shfl_xor_sync(0xffffffffu, sa, o),
-                         tb = __shfl_xor_sync(0xffffffffu, sb, o);
-            sl = (q & o) ? tl + sl : sl + tl; sa = (q & o) ? ta + sa : sa + ta; sb = (q & o) ? tb + sb : sb + tb;
+        for (int o = 16; o > 0; o >>= 1) {
+            sl += __shfl_xor_sync(0xffffffffu, sl, o);
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
         }
-        if (q == 0 && slot < n && cnt != 0u) {
-            const int k = cand[slot].k;
-            atomicAdd(&s.acc_n[3 * k], (u64)cnt);
-            atomicAdd(&s.acc_n[3 * k + 1], (u64)sy);
-            atomicAdd(&s.acc_n[3 * k + 2], (u64)sx);
-            atomicAdd(&s.acc_c[3 * k], sl);
-            atomicAdd(&s.acc_c[3 * k + 1], sa);
-            atomicAdd(&s.acc_c[3 * k + 2], sb);
+        if (lane == leader) {
+            atomicAdd(&s.acc_n[3 * key], (u64)__popc(grp));
+            atomicAdd(&s.acc_n[3 * key + 1], (u64)sy);
+            atomicAdd(&s.acc_n[3 * key + 2], (u64)sx);
+            atomicAdd(&s.acc_c[3 * key], sl);
+            atomicAdd(&s.acc_c[3 * key + 1], sa);
+            atomicAdd(&s.acc_c[3 * key + 2], sb);
         }
+        todo &= ~grp;
     }
     // ---- the last block to finish updates the centres and re-bins them ---------
     __threadfence();
@@ -550,6 +530,7 @@ extern "C" int wesup_slic(const float *rgb, int rgb_layout, int H, int W, int n_
                   "wesup_slic: bad argument H=%d W=%d n_segments=%d compactness=%g", H, W, n_segments, compactness);
     WESUP_REQUIRE(rgb_layout == WESUP_CHW || rgb_layout == WESUP_HWC, WESUP_E_ARG, "wesup_slic: bad layout %d", rgb_layout);
     WESUP_REQUIRE((long)H * W < (1L << 31), WESUP_E_UNSUPPORTED, "wesup_slic: H*W must fit int32");
+    WESUP_REQUIRE(H < 65536 && W < 65536, WESUP_E_UNSUPPORTED, "wesup_slic: H and W must be below 65536");
     int step, start, ny, nx;
     long K = slic_grid(H, W, n_segments, &step, &start, &ny, &nx);
     WESUP_REQUIRE(K > 0, WESUP_E_UNSUPPORTED, "wesup_slic: degenerate seed grid for %dx%d / %d segments", H, W, n_segments);
