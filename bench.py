@@ -296,7 +296,7 @@ def run_own(args):
     torch.manual_seed(0)
     lib = _lib.load()
     trainer = initialize_trainer("wesup", device=dev, pretrained=False, materialize_hypercolumn=args.materialize,
-                                 pool_first=not args.no_pool_first)
+                                 pool_first=not args.no_pool_first, cuda_graph=not args.no_graph)
     trainer.optimizer, _ = trainer.get_default_optimizer()
     trainer.metric_funcs = [accuracy, dice]
     if world > 1:
@@ -410,6 +410,7 @@ def run_own(args):
                        "images_per_step": ips, "images_per_step_all_ranks": ips * world, "hypercolumn": "f32 pixel-major (H*W,2112)" if args.materialize else
                        ("not materialised: superpixel means from the 13 side outputs" if args.no_pool_first else
                         "not materialised: superpixel means from the 13 backbone levels (4224 ch), side convs on the N pooled rows"),
+                       "iteration": "eager" if args.no_graph else "one CUDA graph per image shape (SLIC .. SGD step), replayed",
                        "parallelism": f"dp{world}", "l2": "working set 1.8 GB/image (hypercolumn) >> 126 MB L2; "
                        "kernel microbenches flush L2 with a 256 MB write before every launch",
                        "cudnn_tf32": bool(torch.backends.cudnn.allow_tf32)},
@@ -423,8 +424,8 @@ def run_own(args):
 
 
 def main():
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "WARN"        # no version banner: stdout carries the one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -436,6 +437,8 @@ def main():
                          "superpixel means straight from the backbone levels, side convs on the pooled rows)")
     ap.add_argument("--no-pool-first", action="store_true",
                     help="fused path over the 13 side outputs (side convs on H*W pixels) instead of pool-first")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="eager iterations (default: one CUDA graph per image shape, captured after two eager iterations)")
     ap.add_argument("--no-prefetch", action="store_true", help="preprocess inline instead of one image ahead on a side stream")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-kernels", action="store_true", help="omit the per-kernel roofline microbench")

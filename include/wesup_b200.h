@@ -179,6 +179,15 @@ int wesup_label_propagate_tc(const float *feats, int N, int D, int n_l, const fl
  * max |approx d2 - exact d2| / (|a|^2 + |b|^2) over the re-evaluated pairs. */
 int wesup_label_propagate_tc_stats(const void *ws, int N, int n_l, unsigned long long *out_host);
 
+/* Same operator with the row counts in DEVICE memory (counts_dev = {n_rows, n_labeled}, both
+ * <= n_max): the launch depends only on the capacity n_max, so one CUDA graph serves images
+ * with different superpixel counts.  feats (n_max, D); y_l (n_max, n_cls), rows >= n_labeled
+ * ignored; y_full (n_max, n_cls) is written completely: rows [n_labeled, n_rows) as y_u above,
+ * all other rows zero (the rows _cross_entropy skips, models/wesup.py:84-90).  Same fp32
+ * arithmetic as wesup_label_propagate_exact. */
+int wesup_label_propagate_dev(const float *feats, int n_max, int D, const int32_t *counts_dev,
+                              const float *y_l, int n_cls, float thr, float *y_full, void *stream);
+
 /* ---- (d) SLIC: replaces skimage.segmentation.slic at models/wesup.py:471-476
  * rgb: fp32 in [0,1], (3,H,W) for WESUP_CHW (what the trainer holds) or (H,W,3).
  * labels: (H*W) int32, 0-based, contiguous, numbered in raster order of first

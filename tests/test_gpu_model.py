@@ -8,7 +8,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import wesup_ref as O                      # noqa: E402
-from wesup_b200 import synth                            # noqa: E402
+from wesup_b200 import ops, synth                            # noqa: E402
 from wesup_b200.models import WESUP, WESUPPixelInference, WESUPTrainer, initialize_trainer  # noqa: E402
 from wesup_b200.models.wesup import _cross_entropy, _label_propagate, _preprocess_superpixels  # noqa: E402
 from wesup_b200.ops import SuperpixelMaps              # noqa: E402
@@ -236,3 +236,49 @@ def test_metrics_lag_zero_reads_in_the_same_iteration_and_nan_raises():
     lagged.train_one_iteration("train", *b)
     with pytest.raises(ValueError, match="Loss is nan!"):
         lagged.flush_metrics()
+
+
+def test_cuda_graph_iteration_matches_the_eager_iteration():
+    """cuda_graph=True: one captured graph per input shape (SLIC -> ... -> SGD step), replayed for images with
+    different superpixel / labeled counts; losses, metrics and parameters follow the eager trainer's."""
+    from wesup_b200.utils.metrics import accuracy, dice
+    data = [synth.sample(96, 112, index=i, ratio=2e-3) for i in (3, 4, 5)]
+
+    def run(graph):
+        trainer = initialize_trainer("wesup", device=DEV, pretrained=False, materialize_hypercolumn=False,
+                                     cuda_graph=graph, cuda_graph_after=1)
+        O.seeded_init_(trainer.model, seed=11)
+        trainer.optimizer, _ = trainer.get_default_optimizer()
+        trainer.optimizer.param_groups[0]["lr"] = 1e-3          # large enough for the updates to matter within 6 steps
+        trainer.metric_funcs = [accuracy, dice]
+        for i in range(6):
+            trainer.train_one_iteration("train", *data[i % 3])
+        trainer.flush_metrics()
+        return trainer
+
+    eager, graphed = run(False), run(True)
+    assert 1 <= len(graphed._graphs) <= 3                          # one graph per (shape, 64-row capacity bucket)
+    he, hg = eager.tracker.history, graphed.tracker.history
+    assert set(he) == set(hg)
+    for key in he:
+        assert len(he[key]) == len(hg[key]) == 6
+        np.testing.assert_allclose(hg[key], he[key], rtol=2e-3, atol=1e-5, err_msg=key)   # fp32 summation order differs (padded rows); it compounds over the steps
+        np.testing.assert_allclose(hg[key][:2], he[key][:2], rtol=2e-5, atol=1e-6, err_msg=key)
+    assert len(set(np.round(he["labeled_sp_ratio"], 6))) > 1        # the replayed images really differ in their counts
+    for (name, a), (_, b) in zip(eager.model.named_parameters(), graphed.model.named_parameters()):
+        assert float((a - b).norm() / (a.norm() + 1e-12)) < 1e-4, name
+
+
+def test_label_propagate_static_equals_the_sliced_call():
+    g = torch.Generator().manual_seed(5)
+    n_max, n, n_l = 300, 211, 17
+    f = (torch.randn(n_max, 32, generator=g) * 0.06).to(DEV)
+    y = torch.zeros(n_max, 2)
+    y[torch.arange(n_l), torch.randint(0, 2, (n_l,), generator=g)] = 1
+    y = y.to(DEV)
+    counts = torch.tensor([n, n_l], dtype=torch.int32, device=DEV)
+    full = ops.label_propagate_static(f, y, counts, 0.8)
+    ref = ops.label_propagate(f[:n], y[:n_l], 0.8, algo="exact")
+    assert torch.equal(full[n_l:n], ref)
+    assert float(full[:n_l].abs().sum()) == 0 and float(full[n:].abs().sum()) == 0
+    assert float(ref.sum()) > 0

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--images", type=int, default=8)
     ap.add_argument("--no-materialize", action="store_true")
     ap.add_argument("--no-pool-first", action="store_true")
+    ap.add_argument("--graph", action="store_true")
     ap.add_argument("--host", action="store_true", help="also print where the host time goes")
     ap.add_argument("--size", type=int, nargs=2, default=[bench.H, bench.W])
     a = ap.parse_args()
@@ -33,7 +34,7 @@ def main():
     torch.manual_seed(0)
     h, w = a.size
     trainer = initialize_trainer("wesup", device=dev, pretrained=False, materialize_hypercolumn=not a.no_materialize,
-                                 pool_first=not a.no_pool_first)
+                                 pool_first=not a.no_pool_first, cuda_graph=a.graph)
     trainer.optimizer, _ = trainer.get_default_optimizer()
     trainer.metric_funcs = [accuracy, dice]
     pool = 4

@@ -89,9 +89,91 @@ __global__ void __launch_bounds__(LP_THREADS) label_propagate_generic_kernel(
     if (max_sim) max_sim[u] = best;
 }
 
+// Row counts read from DEVICE memory (counts_dev = {n_rows, n_labeled}): the launch shape
+// depends only on the capacity n_max, so the call can sit in a CUDA graph that is replayed
+// for images with different superpixel counts.  Writes ALL n_max rows of y_full: rows
+// [n_labeled, n_rows) get the propagated label (or zeros below the threshold), every other
+// row zeros -- exactly the rows _cross_entropy ignores (/root/reference/models/wesup.py:84-90).
+template <int D>
+__global__ void __launch_bounds__(LP_THREADS) label_propagate_dev_kernel(
+    const float *__restrict__ feats, int n_max, int D_rt, const int32_t *__restrict__ counts_dev, const float *__restrict__ y_l,
+    int n_cls, float thr, float *__restrict__ y_full) {
+    __shared__ float tile[LP_TILE * (D > 0 ? D : 1)];
+    const int n_rows = min(__ldg(counts_dev), n_max), n_l = min(__ldg(counts_dev + 1), n_rows);
+    const int r = blockIdx.x * LP_THREADS + threadIdx.x;
+    const bool in_range = r < n_max;
+    const bool live = in_range && r >= n_l && r < n_rows;
+    float best = -1.0f;
+    int best_j = 0;
+    if (D > 0) {
+        float f[D > 0 ? D : 1];
+        if (live) {
+            const float4 *row = reinterpret_cast<const float4 *>(feats + (long)r * D);
+#pragma unroll
+            for (int k = 0; k < D / 4; ++k) {
+                float4 v = __ldg(row + k);
+                f[4 * k] = v.x; f[4 * k + 1] = v.y; f[4 * k + 2] = v.z; f[4 * k + 3] = v.w;
+            }
+        }
+        // blocks that hold no unlabeled row skip the scan (block-uniform: derived from blockIdx and the counts)
+        const int r0 = blockIdx.x * LP_THREADS;
+        const bool block_live = r0 < n_rows && r0 + LP_THREADS > n_l;
+        for (int j0 = 0; block_live && j0 < n_l; j0 += LP_TILE) {
+            int rows = min(LP_TILE, n_l - j0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < rows * (D / 4); i += LP_THREADS)
+                reinterpret_cast<float4 *>(tile)[i] = __ldg(reinterpret_cast<const float4 *>(feats + (long)j0 * D) + i);
+            __syncthreads();
+            if (live) {
+                for (int j = 0; j < rows; ++j) {
+                    const float *lrow = tile + j * D;
+                    float d2 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        float t = f[k] - lrow[k];
+                        d2 = fmaf(t, t, d2);
+                    }
+                    float sim = expf(-d2);
+                    if (sim > best) { best = sim; best_j = j0 + j; }
+                }
+            }
+        }
+    } else if (live) {
+        const float *fu = feats + (long)r * D_rt;
+        for (int j = 0; j < n_l; ++j) {
+            const float *fj = feats + (long)j * D_rt;
+            float d2 = 0.f;
+            for (int k = 0; k < D_rt; ++k) {
+                float t = __ldg(fu + k) - __ldg(fj + k);
+                d2 = fmaf(t, t, d2);
+            }
+            float sim = expf(-d2);
+            if (sim > best) { best = sim; best_j = j; }
+        }
+    }
+    if (in_range) {
+        const bool take = live && n_l > 0 && best > thr;
+        for (int c = 0; c < n_cls; ++c) y_full[(long)r * n_cls + c] = take ? __ldg(y_l + (long)best_j * n_cls + c) : 0.f;
+    }
+}
+
 }  // namespace wesup
 
 using namespace wesup;
+
+extern "C" int wesup_label_propagate_dev(const float *feats, int n_max, int D, const int32_t *counts_dev, const float *y_l,
+                                         int n_cls, float thr, float *y_full, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WESUP_REQUIRE(feats && counts_dev && y_l && y_full, WESUP_E_ARG, "wesup_label_propagate_dev: null pointer");
+    WESUP_REQUIRE(n_max > 0 && D > 0 && n_cls > 0, WESUP_E_ARG, "wesup_label_propagate_dev: bad size n_max=%d D=%d n_cls=%d", n_max, D, n_cls);
+    const int grid = cdiv(n_max, LP_THREADS);
+    if (D == 32 && aligned16(feats))
+        label_propagate_dev_kernel<32><<<grid, LP_THREADS, 0, stream>>>(feats, n_max, D, counts_dev, y_l, n_cls, thr, y_full);
+    else
+        label_propagate_dev_kernel<0><<<grid, LP_THREADS, 0, stream>>>(feats, n_max, D, counts_dev, y_l, n_cls, thr, y_full);
+    WESUP_CHECK_LAUNCH("wesup_label_propagate_dev", 1);
+    return 0;
+}
 
 extern "C" size_t wesup_label_propagate_tc_workspace_bytes(int N, int D, int n_l);
 extern "C" int wesup_label_propagate_tc(const float *feats, int N, int D, int n_l, const float *y_l, int n_cls, float thr,

@@ -490,7 +490,11 @@ template <int V>
 static void launch_bwd(const Levels &L, const Groups &G, int g, int stage_cap, const float *gp, const int32_t *row_labels,
                        const int32_t *counts, cudaStream_t stream) {
     const size_t smem = (size_t)PB_WARPS * (stage_cap + PB_LIST) * sizeof(Staged);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(levels_pool_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t allowed = 48 * 1024;              // per instantiation; raised once, outside any stream capture in practice
+    if (smem > allowed) {
+        cudaFuncSetAttribute(levels_pool_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        allowed = smem;
+    }
     const long cells = (long)G.h[g] * G.w[g];
     levels_pool_bwd_kernel<V><<<cdiv(cells, PB_WARPS), PB_WARPS * 32, smem, stream>>>(L, G, g, stage_cap, gp, row_labels, counts);
 }

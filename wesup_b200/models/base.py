@@ -122,6 +122,10 @@ class BaseTrainer(ABC):
         ValueError('Loss is nan!') when its scalars are read -- uncaught by the epoch loop, as
         in the reference; `metrics_lag=0` restores the reference's same-iteration check."""
         input_, target = self.preprocess(*data)
+        self._run_iteration(phase, input_, target)
+
+    def _run_iteration(self, phase, input_, target):
+        """Everything of `train_one_iteration` after `preprocess`."""
         if self.grad_sync is not None:
             self.grad_sync.zero_grad()       # keeps .grad as views of the flat all-reduce buffer
         else:

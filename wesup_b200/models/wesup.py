@@ -373,6 +373,138 @@ class WESUPTrainer(BaseTrainer):
                 t.record_stream(main)
         self._prefetched[key] = (tuple(data), staged, done)
 
+    # ---- CUDA-graph iteration ---------------------------------------------
+    # The eager iteration is host-bound on a B200 (~380 launches per image).  With `cuda_graph=True`
+    # everything after preprocessing -- VGG16, superpixel stage, loss, backward, SGD step, metrics --
+    # is captured ONCE per (input shape, superpixel capacity) and replayed.  Preprocessing (H2D copy,
+    # GPU SLIC, superpixel statistics) keeps running one image ahead on the side stream, which is
+    # also where the host learns the image's superpixel count N without stalling.  The capacity is
+    # N rounded up to a multiple of 64: the graph's per-superpixel buffers have that many rows, the
+    # rows beyond N are empty superpixels (zero features, zero labels, zero gradient), and label
+    # propagation reads N and the labeled count from device memory.  Loss, metrics and updates equal
+    # the eager iteration's up to fp32 summation order.  Hyper-parameters are baked into a graph;
+    # it is re-captured when the learning rate changes.
+    GRAPH_ROW_QUANTUM = 64
+
+    def _static_iteration(self, st, step=True):
+        sp = st["sp"]
+        if self.grad_sync is not None:
+            self.grad_sync.zero_grad()
+        pred = self.model((st["img"], sp))
+        sp_pred, sp_features, y_l = self.model.sp_pred, self.model.sp_features, sp.sp_labels_full
+        counts_dev = st["counts_dev"]
+        metrics = {"labeled_sp_ratio": counts_dev[1].float() / counts_dev[0].float()}
+        loss = self.xentropy(sp_pred, y_l)                      # all-zero rows are ignored by the loss itself
+        if self.kwargs.get("enable_propagation"):
+            y_u = ops.label_propagate_static(sp_features, y_l, counts_dev, self.kwargs.get("propagate_threshold"))
+            propagate_loss = self.xentropy(sp_pred, y_u)
+            loss = loss + self.kwargs.get("propagate_weight") * propagate_loss
+            metrics["propagated_labels"] = y_u.sum()
+            metrics["propagate_loss"] = propagate_loss.detach()
+        self.model.sp_pred = None
+        metrics["loss"] = loss.detach()
+        loss.backward()
+        if step and self.grad_sync is None:
+            self.optimizer.step()
+        self._defer_scalars = True
+        try:
+            labels, target = self.postprocess(pred, (st["pixel_mask"], None))
+            metrics.update(self.evaluate(labels, target))
+        finally:
+            self._defer_scalars = False
+        keys = list(metrics)
+        return keys, torch.stack([metrics[k].detach().float().reshape(()) for k in keys])
+
+    @staticmethod
+    def _load_static(st, img, pixel_mask, sp):
+        """Copy one preprocessed image into a graph's input buffers (device-to-device, a few KB..MB)."""
+        n, hw = sp.n, sp.height * sp.width
+        st["img"].copy_(img, non_blocking=True)
+        st["pixel_mask"].copy_(pixel_mask, non_blocking=True)
+        dst = st["sp"]
+        dst.row_labels.copy_(sp.row_labels, non_blocking=True)
+        dst.seg_pixels.copy_(sp.seg_pixels, non_blocking=True)
+        dst.counts.zero_()
+        dst.counts[:n].copy_(sp.counts, non_blocking=True)
+        dst.seg_offsets.fill_(hw)
+        dst.seg_offsets[:n + 1].copy_(sp.seg_offsets, non_blocking=True)
+        dst.sp_labels_full.zero_()
+        dst.sp_labels_full[:n].copy_(sp.sp_labels_full, non_blocking=True)
+        st["counts_dev"].copy_(sp.counts_dev, non_blocking=True)
+
+    def _capture(self, img, pixel_mask, sp, cap, pool):
+        dev, i32 = img.device, dict(dtype=torch.int32, device=img.device)
+        hw = sp.height * sp.width
+        static_sp = SuperpixelMaps(sp.height, sp.width, cap, None, torch.empty(hw, **i32), torch.empty(cap, **i32),
+                                   torch.empty(cap + 1, **i32), torch.empty(hw, **i32),
+                                   torch.empty(cap, sp.sp_labels_full.size(1), device=dev), None)
+        st = {"img": torch.empty_like(img), "pixel_mask": torch.empty_like(pixel_mask), "sp": static_sp,
+              "counts_dev": torch.empty(2, **i32)}
+        self._load_static(st, img, pixel_mask, sp)
+        self.flush_metrics()
+        # autograd caches one AccumulateGrad node per parameter, bound to the stream of the forward that
+        # created it, for as long as a graph that uses it is alive: drop the eager iteration's graph (the
+        # module caches sp_features) so that warm-up and capture, both on `side`, create fresh ones
+        self.model.sp_features = self.model.sp_pred = self.model.feature_maps = None
+        torch.cuda.synchronize(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                       # warm-up of the static path: no parameter update
+            self._static_iteration(st, step=False)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        if self.grad_sync is None:
+            self.optimizer.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side, **({"pool": pool} if pool is not None else {})):
+            keys, out = self._static_iteration(st, step=True)
+        return {"graph": graph, "st": st, "keys": keys, "out": out, "lr": self.optimizer.param_groups[0]["lr"]}
+
+    def train_one_iteration(self, phase, *data):
+        use_graph = (phase == "train" and self.kwargs.get("cuda_graph", False) and len(data) in (2, 3)
+                     and torch.cuda.is_available() and self.optimizer is not None
+                     and all(torch.is_tensor(d) and not is_empty_tensor(d) for d in data))
+        if not use_graph:
+            return super().train_one_iteration(phase, *data)
+        if not hasattr(self, "_graphs"):
+            self._graphs, self._graph_seen, self._graph_failed, self._graph_pool = {}, {}, set(), None
+        input_, target = self.preprocess(*data)
+        (img, sp), (pixel_mask, _) = input_, target
+        shape_key = tuple((tuple(d.shape), d.dtype) for d in data)
+        q = self.GRAPH_ROW_QUANTUM
+        cap = -(-sp.n // q) * q
+        key = (shape_key, cap)
+        seen = self._graph_seen.get(shape_key, 0)
+        self._graph_seen[shape_key] = seen + 1
+        entry = self._graphs.get(key)
+        if entry is not None and entry["lr"] != self.optimizer.param_groups[0]["lr"]:
+            entry = None                                    # baked hyper-parameter changed: capture again
+        # the first iterations of a shape run eagerly (cuDNN/cuBLAS set-up, momentum buffers)
+        eager = (key in self._graph_failed or sp.counts_dev is None or sp.sp_labels_full is None
+                 or seen < int(self.kwargs.get("cuda_graph_after", 2)) or len(self.optimizer.state) == 0)
+        if not eager and entry is None:
+            try:
+                entry = self._graphs[key] = self._capture(img, pixel_mask, sp, cap, self._graph_pool)
+                if self._graph_pool is None:
+                    self._graph_pool = entry["graph"].pool()      # later graphs replay one at a time: share the memory
+            except Exception as ex:  # noqa: BLE001  (capture is an optimisation: never lose the iteration to it)
+                warnings.warn(f"CUDA-graph capture of the training iteration failed ({type(ex).__name__}: {ex}); "
+                              "this shape keeps running eagerly")
+                self._graph_failed.add(key)
+                self._graphs.pop(key, None)
+                self.model.sp_features = self.model.sp_pred = None
+                self.optimizer.zero_grad(set_to_none=True)
+                torch.cuda.synchronize()
+                eager = True
+        if eager:
+            return self._run_iteration(phase, input_, target)
+        self._load_static(entry["st"], img, pixel_mask, sp)
+        entry["graph"].replay()
+        if self.grad_sync is not None:
+            self.grad_sync.average_gradients()
+            self.optimizer.step()
+        self._submit_scalars(dict(zip(entry["keys"], entry["out"].unbind(0))), phase)
+        self.flush_metrics(keep=max(int(self.kwargs.get("metrics_lag", 1) or 0), 0))
+
     def compute_loss(self, pred, target, metrics=None):
         _, sp_labels = target
         sp_features = self.model.sp_features

@@ -52,6 +52,7 @@ class SuperpixelMaps:
         self.order, self.row_labels, self.counts = order, row_labels, counts
         self.seg_offsets, self.seg_pixels = seg_offsets, seg_pixels
         self.sp_labels_full = sp_labels            # (n, n_cls) incl. zero rows, or None
+        self.counts_dev = None                     # int32 {n, n_labeled} on the device when known there
         self._n_labeled_dev = n_labeled_dev
         self._n_labeled: Optional[int] = None
 
@@ -163,7 +164,7 @@ class PendingSuperpixelMaps:
     host scalars (true count, labeled count) are still in flight."""
 
     def __init__(self, sp: SuperpixelMaps, scalars_dev: torch.Tensor, has_labels: bool):
-        self.sp, self.has_labels = sp, has_labels
+        self.sp, self.has_labels, self.scalars_dev = sp, has_labels, scalars_dev
         self.host = torch.empty(2, dtype=torch.int32, pin_memory=True)
         self.host.copy_(scalars_dev, non_blocking=True)
         self.event = torch.cuda.Event()
@@ -172,7 +173,7 @@ class PendingSuperpixelMaps:
     def tensors(self):
         sp = self.sp
         return [t for t in (sp.order, sp.row_labels, sp.counts, sp.seg_offsets, sp.seg_pixels, sp.sp_labels_full,
-                            sp._n_labeled_dev) if t is not None]
+                            sp._n_labeled_dev, self.scalars_dev) if t is not None]
 
     def finish(self) -> SuperpixelMaps:
         self.event.synchronize()                               # the one host wait per image
@@ -185,6 +186,7 @@ class PendingSuperpixelMaps:
             sp.sp_labels_full = sp.sp_labels_full[:n_true]
         sp.n = n_true
         sp._n_labeled = int(n_labeled) if self.has_labels else 0
+        sp.counts_dev = self.scalars_dev            # int32 {n_true, n_labeled} on the device
         return sp
 
 
@@ -411,6 +413,26 @@ def label_propagate(features: torch.Tensor, y_l: torch.Tensor, threshold: float 
     if return_stats:
         result = result + (stats,)
     return result if len(result) > 1 else result[0]
+
+
+def label_propagate_static(features: torch.Tensor, y_l_full: torch.Tensor, counts_dev: torch.Tensor,
+                           threshold: float = 0.95) -> torch.Tensor:
+    """`label_propagate` for fixed-capacity buffers whose true row counts live on the device
+    (`counts_dev` = int32 {n_rows, n_labeled}): returns y_full (n_max, C) with the propagated
+    labels in rows [n_labeled, n_rows) and zeros elsewhere.  No host scalar is needed, so the
+    call can be captured in a CUDA graph and replayed for other images."""
+    lib = _lib.load()
+    features = features.detach().contiguous().float()
+    y_l_full = y_l_full.detach().contiguous().float()
+    _require_cuda(features, "features")
+    n_max, d = features.shape
+    if y_l_full.size(0) != n_max or counts_dev.dtype != torch.int32 or counts_dev.numel() < 2:
+        raise ValueError("y_l_full must have n_max rows and counts_dev must be int32 {n_rows, n_labeled}")
+    y_full = torch.empty((n_max, y_l_full.size(1)), dtype=torch.float32, device=features.device)
+    check(lib.wesup_label_propagate_dev(features.data_ptr(), n_max, d, counts_dev.data_ptr(), y_l_full.data_ptr(),
+                                        y_l_full.size(1), float(threshold), y_full.data_ptr(), _stream()),
+          "wesup_label_propagate_dev")
+    return y_full
 
 
 # ---------------------------------------------------------------------------
