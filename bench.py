@@ -242,8 +242,9 @@ def kernel_rooflines(dev, peak_gbs):
                 gl = [torch.empty_like(t) for t in lv_mem]
                 gptrs = ops._lib.ptr_array([t.data_ptr() for t in gl])
                 gpl = torch.randn(n_sp, ctot, device=dev)
+                lws = torch.empty(lib.wesup_levels_pool_bwd_workspace_bytes(lca, ha, wa, 13, H, W), dtype=torch.uint8, device=dev)
                 ms = time_kernel(lambda: lib.wesup_levels_pool_bwd(gpl.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
-                                                                   lca, ha, wa, 13, H, W, n_sp, gptrs, st), 10, flush)
+                                                                   lca, ha, wa, 13, H, W, n_sp, gptrs, lws.data_ptr(), st), 10, flush)
                 b = lv_bytes + hw * 4 + n_sp * ctot * 4 + n_sp * 4
                 out[f"levels_pool_bwd_{tag}"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
                 del lv_mem, gl, gpl, pooled_l

@@ -118,14 +118,18 @@ int wesup_levels_pool_fwd(const void *const *level, const int *C, const int *h, 
 /* adjoint of the above (what autograd derives for the mm at models/wesup.py:284-285
  * followed by the cat + interpolate chain at :254-261), evaluated from the pooled
  * gradient (N, sum C): grad_level[l] (fp32 (h[l], w[l], C[l]), fully overwritten).
- * One warp per low-resolution cell: walks the cell's footprint of the label map once,
- * then gathers grad_pooled rows of the distinct superpixels it meets.  Deterministic. */
+ * One warp per low-resolution cell: reads the cell's footprint of the label map once, folds
+ * the tap weights per superpixel (hash table, fixed-point integer adds), then gathers the
+ * grad_pooled rows of the superpixels it met in ascending id order.  Deterministic.
+ * `ws` (wesup_levels_pool_bwd_workspace_bytes) holds small per-axis footprint tables. */
+size_t wesup_levels_pool_bwd_workspace_bytes(const int *C, const int *h, const int *w, int n_levels,
+                                             int H, int W);
 int wesup_levels_pool_bwd(const float *grad_pooled, const int32_t *row_labels, const int32_t *counts,
                           const int *C, const int *h, const int *w, int n_levels, int H, int W,
-                          int N, void *const *grad_level, void *stream);
+                          int N, void *const *grad_level, void *ws, void *stream);
 
 /* Historical names of the fused path (same signatures as ABI 3): they now run the two
- * footprint kernels above; `ws` is unused (any pointer, the size function still answers). */
+ * footprint kernels above (`ws` from wesup_sp_pool_hypercolumn_bwd_workspace_bytes serves both). */
 int wesup_hypercolumn_pool_fwd(const void *const *side, const int *C, const int *h, const int *w,
                                int n_levels, int H, int W, const int32_t *seg_offsets,
                                const int32_t *seg_pixels, int N, float *pooled, void *stream);

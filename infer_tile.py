@@ -26,12 +26,9 @@ def predict(trainer, img_path, patch_size, device="cuda", rank=0, world_size=1):
     """(H,W) prediction for one image (rank 0; None on the other ranks)."""
     img = imread(img_path) if not isinstance(img_path, np.ndarray) else img_path
 
-    def step(x):
-        with torch.no_grad():
-            input_, _ = trainer.preprocess(x)
-            return trainer.postprocess(trainer.model(input_))[0].to(torch.uint8)
-
-    return predict_tiles(step, img, patch_size, device, rank, world_size, out_dtype=torch.uint8)
+    # SLIC + superpixel statistics of tile k+1 run on a side stream while tile k is in the network
+    return predict_tiles(trainer.predict_labels, img, patch_size, device, rank, world_size, out_dtype=torch.uint8,
+                         prefetch=trainer.prefetch)
 
 
 def save_predictions(predictions, img_paths, output_dir="predictions"):
@@ -60,6 +57,9 @@ def main(data_dir, model_type="wesup", patch_size=464, checkpoint=None, output_d
         output_dir = Path(checkpoint).expanduser().parent.parent / "results"
         output_dir.mkdir(exist_ok=True)
     device = device or (f"cuda:{local}" if world > 1 else "cuda")
+    # inference never needs the (H*W,2112) tensor: superpixel means straight from the backbone levels,
+    # one CUDA graph per tile shape (both can be overridden from the command line)
+    kwargs = {"materialize_hypercolumn": False, "cuda_graph": True, **kwargs}
     trainer = initialize_trainer(model_type, device=device, **kwargs)
     if checkpoint is not None:
         trainer.load_checkpoint(checkpoint)

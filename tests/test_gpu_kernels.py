@@ -325,8 +325,9 @@ def test_footprint_kernels_match_the_per_pixel_walk_kernels(h, w, n, channels):
     gp = torch.randn(sp.n, ctot, device=DEV)
     ga = [torch.full_like(s, float("nan")) for s in sides]          # every element must be overwritten
     gb = [torch.empty_like(s) for s in sides]
+    wsl = torch.empty(lib.wesup_levels_pool_bwd_workspace_bytes(ca, ha, wa, len(C), h, w), dtype=torch.uint8, device=DEV)
     _levels_call("wesup_levels_pool_bwd", gp.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(), ca, ha, wa, len(C), h, w,
-                 sp.n, _lib.ptr_array([t.data_ptr() for t in ga]), st)
+                 sp.n, _lib.ptr_array([t.data_ptr() for t in ga]), wsl.data_ptr(), st)
     wsb = torch.empty(lib.wesup_sp_pool_hypercolumn_bwd_workspace_bytes(ca, ha, wa, len(C), h, w, sp.n), dtype=torch.uint8, device=DEV)
     _levels_call("wesup_sp_pool_hypercolumn_bwd_walk", gp.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(), ca, ha, wa,
                  len(C), h, w, sp.n, _lib.ptr_array([t.data_ptr() for t in gb]), wsb.data_ptr(), st)

@@ -43,6 +43,8 @@ def main():
     ap.add_argument("--patch", type=int, default=400)
     ap.add_argument("--mode", choices=["sp", "pixel"], default="sp")
     ap.add_argument("--hc-dtype", choices=["fp32", "bf16"], default="fp32")
+    ap.add_argument("--no-graph", action="store_true", help="eager tile steps (default: CUDA graphs)")
+    ap.add_argument("--materialize", action="store_true", help="sp mode: write the (H*W,2112) hypercolumn, then pool it")
     args = ap.parse_args()
     rank, world, local = parallel.init_from_env("nccl")
     torch.cuda.set_device(local)
@@ -52,31 +54,29 @@ def main():
     slide = synthetic_slide(args.size)
     n_tiles = len(tiles.top_left_coordinates(args.size, args.size, args.patch))
     if args.mode == "sp":
-        trainer = initialize_trainer("wesup", device=dev, pretrained=False, hc_dtype=hc_dtype)
+        trainer = initialize_trainer("wesup", device=dev, pretrained=False, hc_dtype=hc_dtype,
+                                     materialize_hypercolumn=args.materialize, cuda_graph=not args.no_graph)
         trainer.model.eval()
-
-        def step(x):
-            with torch.no_grad():
-                input_, _ = trainer.preprocess(x)
-                return trainer.postprocess(trainer.model(input_))[0].to(torch.uint8)
+        step, prefetch = trainer.predict_labels, trainer.prefetch
         out_dtype = torch.uint8
     else:
         model = WESUPPixelInference(pretrained=False, hc_dtype=hc_dtype).to(dev).eval()
 
-        def step(x):
+        def eager(x):
             with torch.no_grad():
                 return model(x)[..., 1]
+        step, prefetch = (eager if args.no_graph else tiles.GraphedStep(eager)), None
         out_dtype = None
     # warm-up on a few tiles (cuDNN autotune, allocator)
     warm = slide[: args.patch * 2, : args.patch * 2]
-    tiles.predict_tiles(step, warm, args.patch, dev, 0, 1, out_dtype=out_dtype)
+    tiles.predict_tiles(step, warm, args.patch, dev, 0, 1, out_dtype=out_dtype, prefetch=prefetch)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    merged = tiles.predict_tiles(step, slide, args.patch, dev, rank, world, out_dtype=out_dtype)
+    merged = tiles.predict_tiles(step, slide, args.patch, dev, rank, world, out_dtype=out_dtype, prefetch=prefetch)
     e.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
@@ -89,7 +89,7 @@ def main():
         print(json.dumps({"metric": f"tiled inference ({args.mode}) tiles/s", "value": n_tiles / (float(ms.item()) / 1e3),
                           "unit": "tiles/s", "n_gpus": world, "tiles": n_tiles, "patch": args.patch, "slide": args.size,
                           "device_ms_max_over_ranks": float(ms.item()), "wall_s_incl_gather_merge": wall,
-                          "hc_dtype": args.hc_dtype, "positive_fraction": float(np.mean(merged > 0.5))}))
+                          "hc_dtype": args.hc_dtype, "graph": not args.no_graph, "positive_fraction": float(np.mean(merged > 0.5))}))
     if world > 1:
         dist.destroy_process_group()
 

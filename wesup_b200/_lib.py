@@ -35,7 +35,8 @@ SIGNATURES = {
     "wesup_sp_pool_hypercolumn_bwd_workspace_bytes": (c_size_t, [_ip, _ip, _ip, c_int, c_int, c_int, c_int]),
     "wesup_sp_pool_hypercolumn_bwd": (c_int, [_vp, _vp, _vp, _ip, _ip, _ip, c_int, c_int, c_int, c_int, POINTER(_vp), _vp, _vp]),
     "wesup_levels_pool_fwd": (c_int, [POINTER(_vp), _ip, _ip, _ip, c_int, c_int, c_int, _vp, _vp, c_int, _vp, _vp]),
-    "wesup_levels_pool_bwd": (c_int, [_vp, _vp, _vp, _ip, _ip, _ip, c_int, c_int, c_int, c_int, POINTER(_vp), _vp]),
+    "wesup_levels_pool_bwd_workspace_bytes": (c_size_t, [_ip, _ip, _ip, c_int, c_int, c_int]),
+    "wesup_levels_pool_bwd": (c_int, [_vp, _vp, _vp, _ip, _ip, _ip, c_int, c_int, c_int, c_int, POINTER(_vp), _vp, _vp]),
     "wesup_hypercolumn_pool_fwd_walk": (c_int, [POINTER(_vp), _ip, _ip, _ip, c_int, c_int, c_int, _vp, _vp, c_int, _vp, _vp]),
     "wesup_sp_pool_hypercolumn_bwd_walk": (c_int, [_vp, _vp, _vp, _ip, _ip, _ip, c_int, c_int, c_int, c_int, POINTER(_vp), _vp, _vp]),
     "wesup_sp_paint": (c_int, [_vp, _vp, c_int, c_int, c_int, _vp, _vp]),

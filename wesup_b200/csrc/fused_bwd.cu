@@ -169,7 +169,8 @@ extern "C" size_t wesup_sp_pool_hypercolumn_bwd_workspace_bytes(const int *C, co
     }
     FusedPlan P;
     plan_fused(P, h, w, n_levels, H, W, N, Ctot);
-    return P.total;
+    const size_t levels = wesup_levels_pool_bwd_workspace_bytes(C, h, w, n_levels, H, W);   // the footprint kernels' tables
+    return P.total > levels ? P.total : levels;
 }
 
 extern "C" int wesup_sp_pool_hypercolumn_bwd_walk(const float *grad_pooled, const int32_t *row_labels, const int32_t *counts,

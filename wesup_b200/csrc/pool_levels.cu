@@ -34,7 +34,6 @@ constexpr int PF_THREADS = 256;
 constexpr int PF_GRID_CAP = 1024;    // cells of a superpixel's low-res weight grid kept in shared memory
 
 constexpr int PB_WARPS = 8;          // backward: one warp per low-res cell
-constexpr int PB_STAGE_MAX = 1536;   // footprint pixels staged in shared memory per warp
 
 // consecutive levels of equal resolution: their channels are contiguous in the pooled row
 struct Groups {
@@ -44,7 +43,13 @@ struct Groups {
     float sy[WESUP_MAX_LEVELS], sx[WESUP_MAX_LEVELS];
     int coff[WESUP_MAX_LEVELS], Cg[WESUP_MAX_LEVELS];
     int ident[WESUP_MAX_LEVELS];
-    float fscale[WESUP_MAX_LEVELS], finv[WESUP_MAX_LEVELS];   // fwd: 2^F and 2^-F of the fixed-point weight sums (0: no grid)
+    float fscale[WESUP_MAX_LEVELS], finv[WESUP_MAX_LEVELS];   // 2^F and 2^-F of the fixed-point weight sums (0: not usable)
+    int blk1[WESUP_MAX_LEVELS];     // bwd: one past the last block of the group inside its launch (coarse groups first)
+    // bwd: per-axis footprint tables in the workspace (built by axis_tables_kernel): first output index,
+    // number of output indices and their tap weights for every low-resolution row / column of the group
+    int32_t *ylo[WESUP_MAX_LEVELS], *yn[WESUP_MAX_LEVELS], *xlo[WESUP_MAX_LEVELS], *xn[WESUP_MAX_LEVELS];
+    float *wy[WESUP_MAX_LEVELS], *wx[WESUP_MAX_LEVELS];
+    int ky[WESUP_MAX_LEVELS], kx[WESUP_MAX_LEVELS];
 };
 
 __device__ __forceinline__ void locate_level(const Levels &L, int l0, int l1, int c, int &l, int &cl) {
@@ -262,62 +267,92 @@ __global__ void __launch_bounds__(PF_THREADS) levels_pool_fwd_kernel(const Level
 }
 
 // ---------------------------------------------------------------------------
-// backward: one warp per low-resolution cell q of a group
+// backward: one warp per low-resolution cell q
 //   grad_level_l[q, c] = sum_k G_k(q) / |S_k| * grad_pooled[k, coff_l + c]
-// The warp walks the cell's high-resolution footprint once (labels + weights,
-// staged in shared memory), then visits the distinct labels in ascending order:
-// a fixed-order reduction gives the label's total weight and every lane gathers
-// its channel groups of that pooled-gradient row.
+// The warp reads the labels of the cell's high-resolution footprint ONCE and folds the
+// tap weights into a 64-slot hash table keyed by superpixel (per-warp, shared memory):
+// the key is claimed with an atomicCAS, the weight is added as a 32-bit fixed-point
+// integer -- commutative, so the table's CONTENT does not depend on thread order.  The
+// occupied slots are then ranked by key (the slot a key lands in does depend on the
+// order), which gives a list sorted by superpixel id: the floating-point gather that
+// follows has a fixed order and the result is bit-reproducible.  All loads of a list
+// entry (count, pooled-gradient row) are independent and issued together.
+// A footprint that meets more than 64 superpixels takes the slow path: distinct labels
+// visited in ascending order, the footprint re-read for each.
 // ---------------------------------------------------------------------------
 struct Staged { int lab; float w; };
-constexpr int PB_LIST = 64;          // distinct superpixels of one cell collected before their rows are gathered
+constexpr int PB_SLOTS = 64;
 
-__device__ __forceinline__ void footprint_range(int i, float scale, int out_size, int &lo, int &hi) {
-    if (!(scale > 0.f)) { lo = 0; hi = out_size - 1; return; }
-    const float inv = 1.0f / scale;
-    lo = (int)floorf((float)(i - 1) * inv) - 1;
-    hi = (int)ceilf((float)(i + 1) * inv) + 1;
-    lo = max(lo, 0);
-    hi = min(hi, out_size - 1);
+__device__ __forceinline__ float tap_weight(int dst, int cell, float scale, int in_size) {
+    const Tap t = bilinear_tap(dst, scale, in_size);
+    return (t.i0 == cell ? t.w0 : 0.f) + (t.i1 == cell ? t.w1 : 0.f);
+}
+
+// blockIdx.y = 2 * group + axis; one thread per low-resolution index: the exact support of the
+// cell among the output indices (bracket from the inverse map, trimmed with the forward's own tap
+// arithmetic) and the tap weights inside it
+__global__ void axis_tables_kernel(const Groups G, int H, int W) {
+    const int g = blockIdx.y >> 1, axis = blockIdx.y & 1;
+    if (G.ident[g]) return;
+    const int in_size = axis ? G.w[g] : G.h[g], out_size = axis ? W : H;
+    const float scale = axis ? G.sx[g] : G.sy[g];
+    const int K = axis ? G.kx[g] : G.ky[g];
+    int32_t *lo_t = axis ? G.xlo[g] : G.ylo[g], *n_t = axis ? G.xn[g] : G.yn[g];
+    float *w_t = axis ? G.wx[g] : G.wy[g];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= in_size) return;
+    int lo = 0, hi = out_size - 1;
+    if (scale > 0.f) {
+        const float inv = 1.0f / scale;
+        lo = max((int)floorf((float)(i - 1) * inv) - 1, 0);
+        hi = min((int)ceilf((float)(i + 1) * inv) + 1, out_size - 1);
+    }
+    while (lo < hi && tap_weight(lo, i, scale, in_size) == 0.f) ++lo;
+    while (hi > lo && tap_weight(hi, i, scale, in_size) == 0.f) --hi;
+    int n = hi - lo + 1;
+    if (n > K) n = K;                 // cannot happen: K bounds the bracket
+    lo_t[i] = lo;
+    n_t[i] = n;
+    for (int k = 0; k < n; ++k) w_t[(long)i * K + k] = tap_weight(lo + k, i, scale, in_size);
 }
 
 template <int V>
-__global__ void __launch_bounds__(PB_WARPS * 32) levels_pool_bwd_kernel(const Levels L, const Groups G, int g, int stage_cap,
+__global__ void __launch_bounds__(PB_WARPS * 32) levels_pool_bwd_kernel(const Levels L, const Groups G, int g_lo, int g_hi,
                                                                         const float *__restrict__ gp,
                                                                         const int32_t *__restrict__ row_labels,
                                                                         const int32_t *__restrict__ counts) {
-    extern __shared__ Staged smem_bwd[];
+    __shared__ int keys_all[PB_WARPS][PB_SLOTS];
+    __shared__ unsigned wfix_all[PB_WARPS][PB_SLOTS];
+    __shared__ Staged list_all[PB_WARPS][PB_SLOTS];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int g = g_hi - 1;                                   // coarse groups own the first blocks
+    while (g > g_lo && (int)blockIdx.x >= G.blk1[g]) --g;
+    const int blk = (int)blockIdx.x - (g == g_hi - 1 ? 0 : G.blk1[g + 1]);
     const int hg = G.h[g], wg = G.w[g];
-    const long q = (long)blockIdx.x * PB_WARPS + wid;
+    const long q = (long)blk * PB_WARPS + wid;
     if (q >= (long)hg * wg) return;
     const int nch4 = G.Cg[g] >> 2, Ctot = L.Ctot, W = L.W;
     const float *__restrict__ gpg = gp + G.coff[g];
-    Staged *st = smem_bwd + (long)wid * stage_cap;
-    Staged *list = smem_bwd + (long)PB_WARPS * stage_cap + wid * PB_LIST;
+    int *keys = keys_all[wid];
+    unsigned *wfix = wfix_all[wid];
+    Staged *list = list_all[wid];
     float4 acc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int i = (int)(q / wg), j = (int)(q - (long)i * wg);
-    const float sy = G.sy[g], sx = G.sx[g];
-    int ylo, yhi, xlo, xhi;
-    footprint_range(i, sy, L.H, ylo, yhi);
-    footprint_range(j, sx, W, xlo, xhi);
-    const int nx = xhi - xlo + 1, nf = (yhi - ylo + 1) * nx;
+    const int ylo = __ldg(G.ylo[g] + i), xlo = __ldg(G.xlo[g] + j);
+    const int nx = __ldg(G.xn[g] + j), nf = __ldg(G.yn[g] + i) * nx;
+    const float *__restrict__ wyt = G.wy[g] + (long)i * G.ky[g];
+    const float *__restrict__ wxt = G.wx[g] + (long)j * G.kx[g];
     const float inv_nx = 1.0f / (float)nx;
-    const bool staged = nf <= stage_cap;
     auto fetch = [&](int t) {
         const int a = __float2int_rd(((float)t + 0.5f) * inv_nx), b = t - a * nx;
-        const int y = ylo + a, x = xlo + b;
-        const Tap ty = bilinear_tap(y, sy, hg), tx = bilinear_tap(x, sx, wg);
-        const float wy = (ty.i0 == i ? ty.w0 : 0.f) + (ty.i1 == i ? ty.w1 : 0.f);
-        const float wx = (tx.i0 == j ? tx.w0 : 0.f) + (tx.i1 == j ? tx.w1 : 0.f);
         Staged s;
-        s.w = wy * wx;
-        s.lab = (s.w != 0.f) ? __ldg(row_labels + (long)y * W + x) : -1;
+        s.w = __ldg(wyt + a) * __ldg(wxt + b);
+        s.lab = (s.w != 0.f) ? __ldg(row_labels + (long)(ylo + a) * W + xlo + b) : -1;
         return s;
     };
-    // gather the rows of the collected superpixels: all loads of an entry are independent
+    // gather the rows of the listed superpixels: all loads of an entry are independent
     auto flush = [&](int nl) {
         __syncwarp();
         for (int e = lane; e < nl; e += 32) {
@@ -357,31 +392,70 @@ __global__ void __launch_bounds__(PB_WARPS * 32) levels_pool_bwd_kernel(const Le
         }
         __syncwarp();
     };
-    int cur = INT_MAX;
-    for (int t = lane; t < nf; t += 32) {
-        const Staged s = fetch(t);
-        if (staged) st[t] = s;
-        if (s.lab >= 0) cur = min(cur, s.lab);
-    }
+    // ---- fold the footprint into the hash table -------------------------------------------
+    keys[lane] = -1; keys[lane + 32] = -1;
+    wfix[lane] = 0u; wfix[lane + 32] = 0u;
     __syncwarp();
-    cur = __reduce_min_sync(0xffffffffu, cur);
-    int nl = 0;
-    while (cur != INT_MAX) {
-        float ws = 0.f;
-        int nxt = INT_MAX;
+    const float fs = G.fscale[g];
+    bool overflow = !(fs > 0.f);
+    if (!overflow) {
         for (int t = lane; t < nf; t += 32) {
-            const Staged s = staged ? st[t] : fetch(t);
-            if (s.lab == cur) ws += s.w;
-            else if (s.lab > cur) nxt = min(nxt, s.lab);
+            const Staged s_ = fetch(t);
+            if (s_.lab < 0) continue;
+            unsigned h = ((unsigned)s_.lab * 2654435761u) >> 26;
+            int probes = 0;
+            for (; probes < PB_SLOTS; ++probes) {
+                const int old = atomicCAS(&keys[h], -1, s_.lab);
+                if (old == -1 || old == s_.lab) { atomicAdd(&wfix[h], __float2uint_rn(s_.w * fs)); break; }
+                h = (h + 1) & (PB_SLOTS - 1);
+            }
+            if (probes == PB_SLOTS) overflow = true;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
-        nxt = __reduce_min_sync(0xffffffffu, nxt);
-        if (lane == 0) { list[nl].lab = cur; list[nl].w = ws; }
-        if (++nl == PB_LIST) { flush(nl); nl = 0; }
-        cur = nxt;
     }
-    flush(nl);
+    overflow = __any_sync(0xffffffffu, overflow);
+    __syncwarp();
+    if (!overflow) {
+        // rank the occupied slots by key -> list sorted by superpixel id
+        const int k0 = keys[lane], k1 = keys[lane + 32];
+        const unsigned occ0 = __ballot_sync(0xffffffffu, k0 >= 0), occ1 = __ballot_sync(0xffffffffu, k1 >= 0);
+        int r0 = 0, r1 = 0;
+        for (unsigned m = occ0; m; m &= m - 1) {
+            const int kk = keys[__ffs(m) - 1];
+            r0 += kk < k0; r1 += kk < k1;
+        }
+        for (unsigned m = occ1; m; m &= m - 1) {
+            const int kk = keys[32 + __ffs(m) - 1];
+            r0 += kk < k0; r1 += kk < k1;
+        }
+        const float finv = G.finv[g];
+        if (k0 >= 0) { list[r0].lab = k0; list[r0].w = (float)wfix[lane] * finv; }
+        if (k1 >= 0) { list[r1].lab = k1; list[r1].w = (float)wfix[lane + 32] * finv; }
+        flush(__popc(occ0) + __popc(occ1));
+    } else {
+        int cur = INT_MAX;
+        for (int t = lane; t < nf; t += 32) {
+            const Staged s_ = fetch(t);
+            if (s_.lab >= 0) cur = min(cur, s_.lab);
+        }
+        cur = __reduce_min_sync(0xffffffffu, cur);
+        int nl = 0;
+        while (cur != INT_MAX) {
+            float ws = 0.f;
+            int nxt = INT_MAX;
+            for (int t = lane; t < nf; t += 32) {
+                const Staged s_ = fetch(t);
+                if (s_.lab == cur) ws += s_.w;
+                else if (s_.lab > cur) nxt = min(nxt, s_.lab);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
+            nxt = __reduce_min_sync(0xffffffffu, nxt);
+            if (lane == 0) { list[nl].lab = cur; list[nl].w = ws; }
+            if (++nl == PB_SLOTS) { flush(nl); nl = 0; }
+            cur = nxt;
+        }
+        flush(nl);
+    }
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         const int c4 = lane + 32 * v;
@@ -480,23 +554,45 @@ static int fill_pool_levels(Levels &L, const char *who, const void *const *ptrs,
     return 0;
 }
 
-static inline int stage_need(float scale, int out_size) {
+static inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
+static inline int table_len(float scale, int out_size) {
     if (!(scale > 0.f)) return out_size;
-    int k = (int)(2.0f / scale) + 6;
-    return k < out_size ? k : out_size;
+    const int k = (int)(2.0f / scale) + 7;
+    return k < out_size + 2 ? k : out_size + 2;
+}
+// carve the per-axis tables of every non-identity group out of `ws` (ws == nullptr: size only)
+static size_t plan_tables(Groups &G, int H, int W, char *ws) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char *p = ws ? ws + off : nullptr; off += up256(bytes); return p; };
+    for (int g = 0; g < G.n; ++g) {
+        G.ky[g] = G.kx[g] = 0;
+        if (G.ident[g]) continue;
+        G.ky[g] = table_len(G.sy[g], H);
+        G.kx[g] = table_len(G.sx[g], W);
+        G.ylo[g] = (int32_t *)take(sizeof(int32_t) * G.h[g]);
+        G.yn[g] = (int32_t *)take(sizeof(int32_t) * G.h[g]);
+        G.wy[g] = (float *)take(sizeof(float) * (size_t)G.h[g] * G.ky[g]);
+        G.xlo[g] = (int32_t *)take(sizeof(int32_t) * G.w[g]);
+        G.xn[g] = (int32_t *)take(sizeof(int32_t) * G.w[g]);
+        G.wx[g] = (float *)take(sizeof(float) * (size_t)G.w[g] * G.kx[g]);
+    }
+    return off > 256 ? off : 256;
 }
 
 template <int V>
-static void launch_bwd(const Levels &L, const Groups &G, int g, int stage_cap, const float *gp, const int32_t *row_labels,
+static void launch_bwd(const Levels &L, Groups &G, int g_lo, int g_hi, const float *gp, const int32_t *row_labels,
                        const int32_t *counts, cudaStream_t stream) {
-    const size_t smem = (size_t)PB_WARPS * (stage_cap + PB_LIST) * sizeof(Staged);
-    static size_t allowed = 48 * 1024;              // per instantiation; raised once, outside any stream capture in practice
-    if (smem > allowed) {
-        cudaFuncSetAttribute(levels_pool_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        allowed = smem;
+    int blocks = 0;
+    for (int g = g_hi - 1; g >= g_lo; --g) {            // coarse groups (longest footprint walks) own the first blocks
+        blocks += cdiv((long)G.h[g] * G.w[g], PB_WARPS);
+        G.blk1[g] = blocks;
     }
-    const long cells = (long)G.h[g] * G.w[g];
-    levels_pool_bwd_kernel<V><<<cdiv(cells, PB_WARPS), PB_WARPS * 32, smem, stream>>>(L, G, g, stage_cap, gp, row_labels, counts);
+    levels_pool_bwd_kernel<V><<<blocks, PB_WARPS * 32, 0, stream>>>(L, G, g_lo, g_hi, gp, row_labels, counts);
+}
+
+static inline int bwd_slots(int Cg) {                   // float4 accumulators per lane the group needs
+    const int v = (Cg / 4 + 31) / 32;
+    return v <= 1 ? 1 : v <= 2 ? 2 : v <= 4 ? 4 : v <= 6 ? 6 : PB_VMAX;
 }
 
 }  // namespace wesup
@@ -523,11 +619,29 @@ extern "C" int wesup_levels_pool_fwd(const void *const *level, const int *C, con
     return 0;
 }
 
+extern "C" size_t wesup_levels_pool_bwd_workspace_bytes(const int *C, const int *h, const int *w, int n_levels, int H, int W) {
+    if (!C || !h || !w || n_levels <= 0 || n_levels > WESUP_MAX_LEVELS || H <= 0 || W <= 0) return 0;
+    Levels L;
+    L.n = n_levels; L.H = H; L.W = W;
+    int off = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        if (C[l] <= 0 || h[l] <= 0 || w[l] <= 0 || C[l] > PB_VMAX * 128) return 0;
+        L.C[l] = C[l]; L.h[l] = h[l]; L.w[l] = w[l]; L.coff[l] = off;
+        L.sy[l] = bilinear_scale(h[l], H); L.sx[l] = bilinear_scale(w[l], W);
+        off += C[l];
+    }
+    L.Ctot = off;
+    Groups G;
+    if (build_groups(G, L) != 0) return 0;
+    return plan_tables(G, H, W, nullptr);
+}
+
 extern "C" int wesup_levels_pool_bwd(const float *grad_pooled, const int32_t *row_labels, const int32_t *counts, const int *C,
                                      const int *h, const int *w, int n_levels, int H, int W, int N, void *const *grad_level,
-                                     void *stream_) {
+                                     void *ws, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    WESUP_REQUIRE(grad_pooled && row_labels && counts && C && h && w && grad_level, WESUP_E_ARG, "wesup_levels_pool_bwd: null pointer");
+    WESUP_REQUIRE(grad_pooled && row_labels && counts && C && h && w && grad_level && ws, WESUP_E_ARG, "wesup_levels_pool_bwd: null pointer");
+    WESUP_REQUIRE(aligned16(ws), WESUP_E_ALIGN, "wesup_levels_pool_bwd: ws must be 16-byte aligned");
     WESUP_REQUIRE(n_levels > 0 && n_levels <= WESUP_MAX_LEVELS, WESUP_E_ARG, "wesup_levels_pool_bwd: n_levels=%d out of range", n_levels);
     WESUP_REQUIRE(H > 0 && W > 0 && N > 0, WESUP_E_ARG, "wesup_levels_pool_bwd: bad size H=%d W=%d N=%d", H, W, N);
     WESUP_REQUIRE((long)H * W < (1L << 31), WESUP_E_UNSUPPORTED, "wesup_levels_pool_bwd: H*W must fit int32");
@@ -537,24 +651,35 @@ extern "C" int wesup_levels_pool_bwd(const float *grad_pooled, const int32_t *ro
     if (rc) return rc;
     Groups G;
     WESUP_REQUIRE(build_groups(G, L) == 0, WESUP_E_UNSUPPORTED, "wesup_levels_pool_bwd: a level has more than %d channels", PB_VMAX * 128);
-    // coarse groups first: their warps carry the longest footprint walks
-    int launched = 0;
-    for (int g = G.n - 1; g >= 0; --g) {
+    plan_tables(G, H, W, static_cast<char *>(ws));
+    int in_max = 1, launched = 0;
+    bool any_table = false;
+    for (int g = 0; g < G.n; ++g)
+        if (!G.ident[g]) { any_table = true; in_max = in_max > G.h[g] ? in_max : G.h[g]; in_max = in_max > G.w[g] ? in_max : G.w[g]; }
+    if (any_table) {
+        axis_tables_kernel<<<dim3(cdiv(in_max, 128), 2 * G.n), 128, 0, stream>>>(G, H, W);
         ++launched;
-        if (G.ident[g]) {
-            const long HW = (long)H * W;
-            const long items = ((HW + 3) / 4) * (G.Cg[g] / 4);
-            levels_pool_bwd_ident_kernel<<<cdiv(items, 256), 256, 0, stream>>>(L, G, g, grad_pooled, row_labels, counts, HW);
-            continue;
-        }
-        const long need = (long)stage_need(G.sy[g], H) * stage_need(G.sx[g], W);
-        const int stage_cap = (int)(need < PB_STAGE_MAX ? need : PB_STAGE_MAX);
-        const int v = (G.Cg[g] / 4 + 31) / 32;
-        if (v <= 1) launch_bwd<1>(L, G, g, stage_cap, grad_pooled, row_labels, counts, stream);
-        else if (v <= 2) launch_bwd<2>(L, G, g, stage_cap, grad_pooled, row_labels, counts, stream);
-        else if (v <= 4) launch_bwd<4>(L, G, g, stage_cap, grad_pooled, row_labels, counts, stream);
-        else if (v <= 6) launch_bwd<6>(L, G, g, stage_cap, grad_pooled, row_labels, counts, stream);
-        else launch_bwd<PB_VMAX>(L, G, g, stage_cap, grad_pooled, row_labels, counts, stream);
+    }
+    // non-identity groups: consecutive groups with the same accumulator width share one launch (coarse first)
+    for (int g_hi = G.n; g_hi > 0;) {
+        if (G.ident[g_hi - 1]) { --g_hi; continue; }
+        const int v = bwd_slots(G.Cg[g_hi - 1]);
+        int g_lo = g_hi - 1;
+        while (g_lo > 0 && !G.ident[g_lo - 1] && bwd_slots(G.Cg[g_lo - 1]) == v) --g_lo;
+        if (v == 1) launch_bwd<1>(L, G, g_lo, g_hi, grad_pooled, row_labels, counts, stream);
+        else if (v == 2) launch_bwd<2>(L, G, g_lo, g_hi, grad_pooled, row_labels, counts, stream);
+        else if (v == 4) launch_bwd<4>(L, G, g_lo, g_hi, grad_pooled, row_labels, counts, stream);
+        else if (v == 6) launch_bwd<6>(L, G, g_lo, g_hi, grad_pooled, row_labels, counts, stream);
+        else launch_bwd<PB_VMAX>(L, G, g_lo, g_hi, grad_pooled, row_labels, counts, stream);
+        ++launched;
+        g_hi = g_lo;
+    }
+    for (int g = 0; g < G.n; ++g) {
+        if (!G.ident[g]) continue;
+        const long HW = (long)H * W;
+        const long items = ((HW + 3) / 4) * (G.Cg[g] / 4);
+        levels_pool_bwd_ident_kernel<<<cdiv(items, 256), 256, 0, stream>>>(L, G, g, grad_pooled, row_labels, counts, HW);
+        ++launched;
     }
     WESUP_CHECK_LAUNCH("wesup_levels_pool_bwd", launched);
     return 0;
@@ -571,6 +696,5 @@ extern "C" int wesup_hypercolumn_pool_fwd(const void *const *side, const int *C,
 extern "C" int wesup_sp_pool_hypercolumn_bwd(const float *grad_pooled, const int32_t *row_labels, const int32_t *counts,
                                              const int *C, const int *h, const int *w, int n_levels, int H, int W, int N,
                                              void *const *grad_side, void *ws, void *stream) {
-    (void)ws;
-    return wesup_levels_pool_bwd(grad_pooled, row_labels, counts, C, h, w, n_levels, H, W, N, grad_side, stream);
+    return wesup_levels_pool_bwd(grad_pooled, row_labels, counts, C, h, w, n_levels, H, W, N, grad_side, ws, stream);
 }

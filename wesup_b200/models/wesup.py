@@ -420,7 +420,8 @@ class WESUPTrainer(BaseTrainer):
         """Copy one preprocessed image into a graph's input buffers (device-to-device, a few KB..MB)."""
         n, hw = sp.n, sp.height * sp.width
         st["img"].copy_(img, non_blocking=True)
-        st["pixel_mask"].copy_(pixel_mask, non_blocking=True)
+        if st["pixel_mask"] is not None:
+            st["pixel_mask"].copy_(pixel_mask, non_blocking=True)
         dst = st["sp"]
         dst.row_labels.copy_(sp.row_labels, non_blocking=True)
         dst.seg_pixels.copy_(sp.seg_pixels, non_blocking=True)
@@ -428,8 +429,9 @@ class WESUPTrainer(BaseTrainer):
         dst.counts[:n].copy_(sp.counts, non_blocking=True)
         dst.seg_offsets.fill_(hw)
         dst.seg_offsets[:n + 1].copy_(sp.seg_offsets, non_blocking=True)
-        dst.sp_labels_full.zero_()
-        dst.sp_labels_full[:n].copy_(sp.sp_labels_full, non_blocking=True)
+        if dst.sp_labels_full is not None:
+            dst.sp_labels_full.zero_()
+            dst.sp_labels_full[:n].copy_(sp.sp_labels_full, non_blocking=True)
         st["counts_dev"].copy_(sp.counts_dev, non_blocking=True)
 
     def _capture(self, img, pixel_mask, sp, cap, pool):
@@ -504,6 +506,52 @@ class WESUPTrainer(BaseTrainer):
             self.optimizer.step()
         self._submit_scalars(dict(zip(entry["keys"], entry["out"].unbind(0))), phase)
         self.flush_metrics(keep=max(int(self.kwargs.get("metrics_lag", 1) or 0), 0))
+
+    # ---- inference on one image / tile ------------------------------------------------------
+    def predict_labels(self, img):
+        """Class map (H,W) uint8 of one image `(1,3,H,W)` -- what infer.py / infer_tile.py compute as
+        `postprocess(model(preprocess(img)))` (/root/reference/infer_tile.py:111-116).  Picks up a
+        `prefetch(img)` issued earlier; with `cuda_graph=True` the network part (VGG16 -> superpixel
+        means -> MLP -> paint -> round) replays one graph per (tile shape, 64-row superpixel capacity)."""
+        with torch.no_grad():
+            (x, sp), _ = self.preprocess(img)
+            if not (self.kwargs.get("cuda_graph", False) and sp.counts_dev is not None):
+                return self.postprocess(self.model((x, sp)))[0].to(torch.uint8)
+            if not hasattr(self, "_infer_graphs"):
+                self._infer_graphs, self._infer_seen, self._infer_pool = {}, {}, None
+            q = self.GRAPH_ROW_QUANTUM
+            cap = -(-sp.n // q) * q
+            key = (tuple(x.shape), cap, self.model.training)
+            entry = self._infer_graphs.get(key)
+            if entry is None:
+                seen = self._infer_seen.get(key[0], 0)
+                self._infer_seen[key[0]] = seen + 1
+                if seen < int(self.kwargs.get("cuda_graph_after", 2)):
+                    return self.postprocess(self.model((x, sp)))[0].to(torch.uint8)
+                entry = self._infer_graphs[key] = self._capture_infer(x, sp, cap)
+            self._load_static(entry["st"], x, None, sp)
+            entry["graph"].replay()
+            return entry["out"].clone()
+
+    def _capture_infer(self, x, sp, cap):
+        dev, i32 = x.device, dict(dtype=torch.int32, device=x.device)
+        hw = sp.height * sp.width
+        static_sp = SuperpixelMaps(sp.height, sp.width, cap, None, torch.empty(hw, **i32), torch.empty(cap, **i32),
+                                   torch.empty(cap + 1, **i32), torch.empty(hw, **i32), None, None)
+        st = {"img": torch.empty_like(x), "pixel_mask": None, "sp": static_sp, "counts_dev": torch.empty(2, **i32)}
+        self._load_static(st, x, None, sp)
+        torch.cuda.synchronize(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self.postprocess(self.model((st["img"], static_sp)))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side, **({"pool": self._infer_pool} if self._infer_pool is not None else {})):
+            out = self.postprocess(self.model((st["img"], static_sp)))[0].to(torch.uint8)
+        if self._infer_pool is None:
+            self._infer_pool = graph.pool()
+        return {"graph": graph, "st": st, "out": out}
 
     def compute_loss(self, pred, target, metrics=None):
         _, sp_labels = target

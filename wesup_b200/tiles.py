@@ -60,28 +60,80 @@ def combine_disjoint(patches: np.ndarray, target_height: int, target_width: int)
     return np.squeeze(grid.transpose(axes).reshape(target_height, target_width, *tail))
 
 
+class GraphedStep:
+    """`step(x)` for a fixed input shape as ONE CUDA graph: the first `warm` calls run eagerly
+    (library set-up), the next one is captured, every later call copies `x` into the graph's
+    input buffer, replays, and returns a copy of the graph's output.  A call with another shape
+    runs eagerly.  For forward-only steps whose launch sequence does not depend on the data
+    (pixel-wise tile inference: VGG16 -> hypercolumn -> per-pixel MLP)."""
+
+    def __init__(self, step, warm: int = 2):
+        self.step, self.warm, self.calls = step, warm, 0
+        self.graph = self.x = self.y = None
+
+    def __call__(self, x):
+        import torch
+        if self.graph is None:
+            self.calls += 1
+            if self.calls <= self.warm or not x.is_cuda:
+                return self.step(x)
+            self.x = x.clone()
+            torch.cuda.synchronize(x.device)
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):
+                self.step(self.x)
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                self.y = self.step(self.x)
+            self.graph = graph
+        if x.shape != self.x.shape or x.dtype != self.x.dtype:
+            return self.step(x)
+        self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.y.clone()
+
+
 def predict_tiles(step, img: np.ndarray, patch_size: int, device, rank: int = 0, world_size: int = 1, group=None,
-                  out_dtype=None):
+                  out_dtype=None, prefetch=None, chunk: int = 256):
     """Run `step(tile_tensor (1,3,p,p) fp32 on device) -> (p,p[,C]) tensor` on the
     tiles this rank owns (contiguous block of the row-major tile list, so a rank's
     output is a stripe of the slide), gather the finished tiles to rank 0 in tile
     order and merge them there.  Returns the merged (H,W[,C]) array on rank 0 and
-    None elsewhere.  Tiles are cut on the host (uint8) and converted to fp32 on
-    the device; nothing but finished predictions travels between ranks
-    (no data-path collective)."""
+    None elsewhere.  Tiles are cut on the host (uint8) `chunk` at a time into one pinned
+    staging buffer, travel to the device in one asynchronous copy per chunk and are
+    converted to fp32 there; nothing but finished predictions travels between ranks
+    (no data-path collective).  `prefetch(x)` (optional) is called
+    with tile k+1's tensor before `step` runs on tile k -- the superpixel-wise path uses it
+    to run GPU SLIC one tile ahead on a side stream."""
     import torch
     from .parallel import gather_tiles, shard_range
     height, width = img.shape[:2]
     coords = top_left_coordinates(height, width, patch_size)
     lo, hi = shard_range(len(coords), rank, world_size)
-    src = torch.from_numpy(np.ascontiguousarray(img[..., :3]))
-    pinned = src.pin_memory() if torch.cuda.is_available() else src
+    mine = coords[lo:hi]
+    use_cuda = torch.cuda.is_available() and torch.device(device).type == "cuda"
     outs = []
-    for t, l in coords[lo:hi]:
-        tile = pinned[t:t + patch_size, l:l + patch_size].to(device, non_blocking=True)
-        x = tile.permute(2, 0, 1).float().div_(255.0).unsqueeze(0).contiguous()       # == TF.to_tensor
-        y = step(x)
-        outs.append(y if out_dtype is None else y.to(out_dtype))
+    for c0 in range(0, len(mine), chunk):
+        part = mine[c0:c0 + chunk]
+        stage = torch.empty((len(part), patch_size, patch_size, 3), dtype=torch.uint8, pin_memory=use_cuda)
+        stage_np = stage.numpy()
+        for k, (t, l) in enumerate(part):
+            stage_np[k] = img[t:t + patch_size, l:l + patch_size, :3]
+        dev_u8 = stage.to(device, non_blocking=True)
+
+        def tile(k):
+            return dev_u8[k].permute(2, 0, 1).float().div_(255.0).unsqueeze(0).contiguous()       # == TF.to_tensor
+
+        x = tile(0)
+        for k in range(len(part)):
+            nxt = tile(k + 1) if k + 1 < len(part) else None
+            if prefetch is not None and nxt is not None:
+                prefetch(nxt)
+            y = step(x)
+            outs.append(y if out_dtype is None else y.to(out_dtype))
+            x = nxt
     if outs:
         local = torch.stack(outs)
     else:
