@@ -317,7 +317,7 @@ __global__ void axis_tables_kernel(const Groups G, int H, int W) {
 }
 
 template <int V>
-__global__ void __launch_bounds__(PB_WARPS * 32) levels_pool_bwd_kernel(const Levels L, const Groups G, int g_lo, int g_hi,
+__global__ void __launch_bounds__(PB_WARPS * 32, V <= 2 ? 5 : (V <= 6 ? 3 : 2)) levels_pool_bwd_kernel(const Levels L, const Groups G, int g_lo, int g_hi,
                                                                         const float *__restrict__ gp,
                                                                         const int32_t *__restrict__ row_labels,
                                                                         const int32_t *__restrict__ counts) {
@@ -352,23 +352,21 @@ __global__ void __launch_bounds__(PB_WARPS * 32) levels_pool_bwd_kernel(const Le
         s.lab = (s.w != 0.f) ? __ldg(row_labels + (long)(ylo + a) * W + xlo + b) : -1;
         return s;
     };
-    // gather the rows of the listed superpixels: all loads of an entry are independent
+    // gather the rows of the listed superpixels: the count and the row of an entry depend only on its
+    // id, so all of them are issued together (the weight meets the count at the FMA)
     auto flush = [&](int nl) {
         __syncwarp();
-        for (int e = lane; e < nl; e += 32) {
-            const int cnt = __ldg(counts + list[e].lab);
-            list[e].w = cnt > 0 ? list[e].w / (float)cnt : 0.f;
-        }
-        __syncwarp();
-        constexpr int U = V >= 6 ? 1 : (V >= 4 ? 2 : 4);
+        constexpr int U = V >= 6 ? 1 : 2;
         int e = 0;
         for (; e + U <= nl; e += U) {
             float4 val[U][V];
             float wv[U];
+            int cnt[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const Staged en = list[e + u];
                 wv[u] = en.w;
+                cnt[u] = __ldg(counts + en.lab);
                 const float4 *__restrict__ row = reinterpret_cast<const float4 *>(gpg + (long)en.lab * Ctot);
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
@@ -377,18 +375,25 @@ __global__ void __launch_bounds__(PB_WARPS * 32) levels_pool_bwd_kernel(const Le
                 }
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u)
+            for (int u = 0; u < U; ++u) {
+                const float wq = cnt[u] > 0 ? wv[u] / (float)cnt[u] : 0.f;
 #pragma unroll
-                for (int v = 0; v < V; ++v) fma4(acc[v], wv[u], val[u][v]);
+                for (int v = 0; v < V; ++v) fma4(acc[v], wq, val[u][v]);
+            }
         }
         for (; e < nl; ++e) {
             const Staged en = list[e];
+            const int cnt = __ldg(counts + en.lab);
             const float4 *__restrict__ row = reinterpret_cast<const float4 *>(gpg + (long)en.lab * Ctot);
+            float4 val[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 const int c4 = lane + 32 * v;
-                if (c4 < nch4) fma4(acc[v], en.w, __ldg(row + c4));
+                val[v] = c4 < nch4 ? __ldg(row + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            const float wq = cnt > 0 ? en.w / (float)cnt : 0.f;
+#pragma unroll
+            for (int v = 0; v < V; ++v) fma4(acc[v], wq, val[v]);
         }
         __syncwarp();
     };
@@ -399,9 +404,8 @@ __global__ void __launch_bounds__(PB_WARPS * 32) levels_pool_bwd_kernel(const Le
     const float fs = G.fscale[g];
     bool overflow = !(fs > 0.f);
     if (!overflow) {
-        for (int t = lane; t < nf; t += 32) {
-            const Staged s_ = fetch(t);
-            if (s_.lab < 0) continue;
+        auto insert = [&](const Staged &s_) {
+            if (s_.lab < 0) return;
             unsigned h = ((unsigned)s_.lab * 2654435761u) >> 26;
             int probes = 0;
             for (; probes < PB_SLOTS; ++probes) {
@@ -410,7 +414,16 @@ __global__ void __launch_bounds__(PB_WARPS * 32) levels_pool_bwd_kernel(const Le
                 h = (h + 1) & (PB_SLOTS - 1);
             }
             if (probes == PB_SLOTS) overflow = true;
+        };
+        int t = lane;
+        for (; t + 96 < nf; t += 128) {                  // four label loads in flight per lane
+            Staged b4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) b4[u] = fetch(t + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) insert(b4[u]);
         }
+        for (; t < nf; t += 32) insert(fetch(t));
     }
     overflow = __any_sync(0xffffffffu, overflow);
     __syncwarp();
@@ -579,6 +592,32 @@ static size_t plan_tables(Groups &G, int H, int W, char *ws) {
     return off > 256 ? off : 256;
 }
 
+// The backward is several latency-bound launches of very different shapes (few heavy cells at the
+// coarse resolutions, many light ones at the fine ones).  They are independent, so they are forked
+// onto auxiliary streams and joined back into the caller's stream -- event dependencies only, which
+// also capture into a CUDA graph as parallel branches.  The auxiliary streams belong to the library
+// (created once per process; calls from several host threads merely share them).
+constexpr int PB_AUX = 3;
+struct AuxStreams {
+    cudaStream_t s[PB_AUX];
+    cudaEvent_t fork, join[PB_AUX];
+    bool ok = false;
+};
+static AuxStreams *aux_streams() {
+    static AuxStreams a;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        bool ok = cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; ok && i < PB_AUX; ++i)
+            ok = cudaStreamCreateWithFlags(&a.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&a.join[i], cudaEventDisableTiming) == cudaSuccess;
+        a.ok = ok;
+        if (!ok) cudaGetLastError();
+    }
+    return a.ok ? &a : nullptr;
+}
+
 template <int V>
 static void launch_bwd(const Levels &L, Groups &G, int g_lo, int g_hi, const float *gp, const int32_t *row_labels,
                        const int32_t *counts, cudaStream_t stream) {
@@ -660,17 +699,27 @@ extern "C" int wesup_levels_pool_bwd(const float *grad_pooled, const int32_t *ro
         axis_tables_kernel<<<dim3(cdiv(in_max, 128), 2 * G.n), 128, 0, stream>>>(G, H, W);
         ++launched;
     }
-    // non-identity groups: consecutive groups with the same accumulator width share one launch (coarse first)
+    // non-identity groups: consecutive groups with the same accumulator width share one launch (coarse
+    // first); launch k runs on auxiliary stream k-1 (the first one and anything beyond the pool on `stream`)
+    AuxStreams *aux = aux_streams();
+    if (aux && cudaEventRecord(aux->fork, stream) != cudaSuccess) aux = nullptr;
+    int n_forked = 0, k_launch = 0;
     for (int g_hi = G.n; g_hi > 0;) {
         if (G.ident[g_hi - 1]) { --g_hi; continue; }
         const int v = bwd_slots(G.Cg[g_hi - 1]);
         int g_lo = g_hi - 1;
         while (g_lo > 0 && !G.ident[g_lo - 1] && bwd_slots(G.Cg[g_lo - 1]) == v) --g_lo;
-        if (v == 1) launch_bwd<1>(L, G, g_lo, g_hi, grad_pooled, row_labels, counts, stream);
-        else if (v == 2) launch_bwd<2>(L, G, g_lo, g_hi, grad_pooled, row_labels, counts, stream);
-        else if (v == 4) launch_bwd<4>(L, G, g_lo, g_hi, grad_pooled, row_labels, counts, stream);
-        else if (v == 6) launch_bwd<6>(L, G, g_lo, g_hi, grad_pooled, row_labels, counts, stream);
-        else launch_bwd<PB_VMAX>(L, G, g_lo, g_hi, grad_pooled, row_labels, counts, stream);
+        cudaStream_t s_launch = stream;
+        if (aux && k_launch > 0 && n_forked < PB_AUX) {
+            s_launch = aux->s[n_forked++];
+            cudaStreamWaitEvent(s_launch, aux->fork, 0);
+        }
+        ++k_launch;
+        if (v == 1) launch_bwd<1>(L, G, g_lo, g_hi, grad_pooled, row_labels, counts, s_launch);
+        else if (v == 2) launch_bwd<2>(L, G, g_lo, g_hi, grad_pooled, row_labels, counts, s_launch);
+        else if (v == 4) launch_bwd<4>(L, G, g_lo, g_hi, grad_pooled, row_labels, counts, s_launch);
+        else if (v == 6) launch_bwd<6>(L, G, g_lo, g_hi, grad_pooled, row_labels, counts, s_launch);
+        else launch_bwd<PB_VMAX>(L, G, g_lo, g_hi, grad_pooled, row_labels, counts, s_launch);
         ++launched;
         g_hi = g_lo;
     }
@@ -680,6 +729,10 @@ extern "C" int wesup_levels_pool_bwd(const float *grad_pooled, const int32_t *ro
         const long items = ((HW + 3) / 4) * (G.Cg[g] / 4);
         levels_pool_bwd_ident_kernel<<<cdiv(items, 256), 256, 0, stream>>>(L, G, g, grad_pooled, row_labels, counts, HW);
         ++launched;
+    }
+    for (int i = 0; i < n_forked; ++i) {
+        cudaEventRecord(aux->join[i], aux->s[i]);
+        cudaStreamWaitEvent(stream, aux->join[i], 0);
     }
     WESUP_CHECK_LAUNCH("wesup_levels_pool_bwd", launched);
     return 0;
