@@ -14,9 +14,9 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 450 -c 
     python bench.py --steps 1 --warmup 1 --images-per-step 2 --skip-cpu --skip-kernels > $out/b_ncu.log 2>&1
 python tools/summarize_launches.py $out/launches.csv > $out/launches_summary.md
 # full ncu capture of the superpixel-stage kernels, one launch each, in two small reports
-K1="hyper_fwd_bulk|pool_fwd_hwc|pool_bwd_walk|levels_pool_fwd|levels_pool_bwd|fused_pool_hyper|fused_hyper_pool_fwd|hyper_bwd_rows|hyper_bwd_cols"
+K1="hyper_fwd_bulk|pool_fwd_hwc|pool_bwd_walk|levels_pool_fwd|levels_pool_bwd|hyper_bwd_rows|hyper_bwd_cols"
 K2="label_propagate_tc|label_propagate_exact|slic_sweep|paint_kernel|stats_accumulate|csr_fill|ccl_small"
-timeout 600 ncu --set full --clock-control none -k regex:"$K1" -c 40 -o $out/prof_hbm python tools/kernels_once.py > $out/ncu_hbm.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$K1" -c 44 -o $out/prof_hbm python tools/kernels_once.py > $out/ncu_hbm.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$K2" -c 14 -o $out/prof_misc python tools/kernels_once.py > $out/ncu_misc.log 2>&1
 python tools/ncu_summary.py $out/prof_hbm.ncu-rep > $out/ncu_hbm_summary.md
 python tools/ncu_summary.py $out/prof_misc.ncu-rep > $out/ncu_misc_summary.md
