@@ -247,7 +247,23 @@ def kernel_rooflines(dev, peak_gbs):
                                                                    lca, ha, wa, 13, H, W, n_sp, gptrs, lws.data_ptr(), st), 10, flush)
                 b = lv_bytes + hw * 4 + n_sp * ctot * 4 + n_sp * 4
                 out[f"levels_pool_bwd_{tag}"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
-                del lv_mem, gl, gpl, pooled_l
+                # the same operators over footprints precomputed once per image (the path the model takes)
+                fpb = torch.empty(lib.wesup_footprint_bytes(ha, wa, 13, H, W, n_sp), dtype=torch.uint8, device=dev)
+                build = lambda: lib.wesup_footprint_build(ha, wa, 13, H, W, n_sp, sp.seg_offsets.data_ptr(), sp.seg_pixels.data_ptr(),  # noqa: E731
+                                                          sp.row_labels.data_ptr(), sp.counts.data_ptr(), 1, fpb.data_ptr(), st)
+                if mult == 2:
+                    ms = time_kernel(build, 10, flush)
+                    out["footprint_build"] = {"ms": ms, "note": "per image, label map only; forked beside the backbone"}
+                build()
+                ms = time_kernel(lambda: lib.wesup_levels_pool_fwd_fp(lptrs, lca, ha, wa, 13, H, W, sp.seg_offsets.data_ptr(),
+                                                                      sp.seg_pixels.data_ptr(), n_sp, fpb.data_ptr(),
+                                                                      pooled_l.data_ptr(), st), 10, flush)
+                b = lv_bytes + hw * 4 + n_sp * ctot * 4 + n_sp * 4
+                out[f"fp_pool_fwd_{tag}"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
+                ms = time_kernel(lambda: lib.wesup_levels_pool_bwd_fp(gpl.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
+                                                                      lca, ha, wa, 13, H, W, n_sp, fpb.data_ptr(), gptrs, st), 10, flush)
+                out[f"fp_pool_bwd_{tag}"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
+                del lv_mem, gl, gpl, pooled_l, fpb
             out["levels_pool_fwd_side2112"]["replaces_ms"] = out["hypercolumn_fwd_f32"]["ms"] + out["sp_pool_fwd_f32"]["ms"]
             out["levels_pool_bwd_side2112"]["replaces_ms"] = out["sp_pool_bwd_f32"]["ms"] + out["hypercolumn_bwd_f32"]["ms"]
         del feats, gf
@@ -297,7 +313,8 @@ def run_own(args):
     torch.manual_seed(0)
     lib = _lib.load()
     trainer = initialize_trainer("wesup", device=dev, pretrained=False, materialize_hypercolumn=args.materialize,
-                                 pool_first=not args.no_pool_first, cuda_graph=not args.no_graph)
+                                 pool_first=not args.no_pool_first, cuda_graph=not args.no_graph,
+                                 footprints=not args.no_footprints)
     trainer.optimizer, _ = trainer.get_default_optimizer()
     trainer.metric_funcs = [accuracy, dice]
     if world > 1:
@@ -375,12 +392,19 @@ def run_own(args):
                 "hyper_fwd_bulk_kernel<float,4> (wesup_hypercolumn_fwd)"
         else:
             tag = "side2112" if args.no_pool_first else "backbone4224"
-            key = max((f"levels_pool_fwd_{tag}", f"levels_pool_bwd_{tag}"), key=lambda k_: kernels[k_]["ms"])
-            if "fwd" in key:
-                name, label = "levels_pool_fwd_kernel(Levels, Groups, const int *, const int *, float *)", \
-                    "levels_pool_fwd_kernel (wesup_levels_pool_fwd)"
+            if args.no_footprints:
+                key = max((f"levels_pool_fwd_{tag}", f"levels_pool_bwd_{tag}"), key=lambda k_: kernels[k_]["ms"])
+                if "fwd" in key:
+                    name, label = "levels_pool_fwd_kernel(Levels, Groups, const int *, const int *, float *)", \
+                        "levels_pool_fwd_kernel (wesup_levels_pool_fwd)"
+                else:
+                    name, label = "levels_pool_bwd_kernel", "levels_pool_bwd_kernel<V> x 5 resolution groups (wesup_levels_pool_bwd)"
             else:
-                name, label = "levels_pool_bwd_kernel", "levels_pool_bwd_kernel<V> x 5 resolution groups (wesup_levels_pool_bwd)"
+                key = max((f"fp_pool_fwd_{tag}", f"fp_pool_bwd_{tag}"), key=lambda k_: kernels[k_]["ms"])
+                if "fwd" in key:
+                    name, label = "fp_pool_fwd_kernel", "fp_pool_fwd_kernel (wesup_levels_pool_fwd_fp)"
+                else:
+                    name, label = "fp_pool_bwd", "fp_pool_bwd_kernel + fp_pool_bwd_ident_kernel (wesup_levels_pool_bwd_fp)"
         k = kernels[key]
         traffic = None
         tfile = ROOT / "profiles" / "roofline_traffic.json"
@@ -411,6 +435,8 @@ def run_own(args):
                        "images_per_step": ips, "images_per_step_all_ranks": ips * world, "hypercolumn": "f32 pixel-major (H*W,2112)" if args.materialize else
                        ("not materialised: superpixel means from the 13 side outputs" if args.no_pool_first else
                         "not materialised: superpixel means from the 13 backbone levels (4224 ch), side convs on the N pooled rows"),
+                       "footprints": "rebuilt inside the pooling kernels" if args.no_footprints else
+                       "precomputed per image (wesup_footprint_build, forked beside the backbone)",
                        "iteration": "eager" if args.no_graph else "one CUDA graph per image shape (SLIC .. SGD step), replayed",
                        "parallelism": f"dp{world}", "l2": "working set 1.8 GB/image (hypercolumn) >> 126 MB L2; "
                        "kernel microbenches flush L2 with a 256 MB write before every launch",
@@ -438,6 +464,8 @@ def main():
                          "superpixel means straight from the backbone levels, side convs on the pooled rows)")
     ap.add_argument("--no-pool-first", action="store_true",
                     help="fused path over the 13 side outputs (side convs on H*W pixels) instead of pool-first")
+    ap.add_argument("--no-footprints", action="store_true",
+                    help="pooling kernels rebuild the superpixel footprints internally (default: built once per image on a side stream)")
     ap.add_argument("--no-graph", action="store_true",
                     help="eager iterations (default: one CUDA graph per image shape, captured after two eager iterations)")
     ap.add_argument("--no-prefetch", action="store_true", help="preprocess inline instead of one image ahead on a side stream")

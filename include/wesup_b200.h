@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define WESUP_ABI_VERSION 4
+#define WESUP_ABI_VERSION 5
 #define WESUP_MAX_LEVELS 16
 
 /* element type of the hypercolumn tensor */
@@ -127,6 +127,32 @@ size_t wesup_levels_pool_bwd_workspace_bytes(const int *C, const int *h, const i
 int wesup_levels_pool_bwd(const float *grad_pooled, const int32_t *row_labels, const int32_t *counts,
                           const int *C, const int *h, const int *w, int n_levels, int H, int W,
                           int N, void *const *grad_level, void *ws, void *stream);
+
+/* ---- the same two operators over PRECOMPUTED footprints ------------------------
+ * The weights G_k(cell) depend only on the label map and the level resolutions: they are
+ * the sparse form of the reference's dense `sp_maps` (models/wesup.py:57-61) composed with
+ * the interpolation of :254-255, and like `sp_maps` they are built once per image in
+ * preprocessing.  wesup_footprint_build fills an opaque device blob `fp`
+ * (wesup_footprint_bytes; depends on h, w, H, W, N only) with, per distinct non-identity
+ * resolution, the forward lists (per superpixel: cells + weights) and -- with_bwd != 0 --
+ * their transpose (per cell: superpixel rows + weights / |S_k|, ascending rows).  The pooling
+ * kernels are then prologue-free streaming gathers; results equal wesup_levels_pool_fwd/bwd
+ * up to fp32 summation order.  `h`, `w`, H, W, N must be the ones the blob was built with;
+ * rows k with an empty CSR segment pool to zero (fixed-capacity callers, CUDA graphs).
+ * Any C[l] % 4 == 0. */
+size_t wesup_footprint_bytes(const int *h, const int *w, int n_levels, int H, int W, int N);
+int wesup_footprint_build(const int *h, const int *w, int n_levels, int H, int W, int N,
+                          const int32_t *seg_offsets, const int32_t *seg_pixels,
+                          const int32_t *row_labels, const int32_t *counts, int with_bwd,
+                          void *fp, void *stream);
+int wesup_levels_pool_fwd_fp(const void *const *level, const int *C, const int *h, const int *w,
+                             int n_levels, int H, int W, const int32_t *seg_offsets,
+                             const int32_t *seg_pixels, int N, const void *fp, float *pooled,
+                             void *stream);
+int wesup_levels_pool_bwd_fp(const float *grad_pooled, const int32_t *row_labels,
+                             const int32_t *counts, const int *C, const int *h, const int *w,
+                             int n_levels, int H, int W, int N, const void *fp,
+                             void *const *grad_level, void *stream);
 
 /* Historical names of the fused path (same signatures as ABI 3): they now run the two
  * footprint kernels above (`ws` from wesup_sp_pool_hypercolumn_bwd_workspace_bytes serves both). */

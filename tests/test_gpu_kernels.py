@@ -346,6 +346,122 @@ def test_footprint_kernels_match_the_per_pixel_walk_kernels(h, w, n, channels):
     assert torch.equal(a, a2)
 
 
+def _scattered_segments(h, w, n, seed):
+    """Every pixel draws its superpixel at random: footprints meet > 64 superpixels (slow path of the
+    backward list builder) and bounding boxes cover the image (per-pixel entries in the forward lists)."""
+    g = torch.Generator().manual_seed(seed)
+    seg = torch.randint(0, n, (h, w), generator=g)
+    seg.view(-1)[:n] = torch.arange(n)
+    return seg
+
+
+@pytest.mark.parametrize("h,w,n,channels,kind", [(48, 40, 30, VGG_C, "grid"), (131, 97, 60, VGG_C, "grid"),
+                                                 (96, 112, 50, FULL_C, "grid"), (464, 464, 1076, FULL_C, "grid"),
+                                                 (200, 180, 3, VGG_C, "grid"), (80, 72, 700, VGG_C, "scattered"),
+                                                 (37, 51, 7, [8, 20, 36], "grid")])
+def test_precomputed_footprint_pooling_matches_the_in_kernel_footprint_kernels(h, w, n, channels, kind):
+    """wesup_footprint_build + wesup_levels_pool_fwd_fp/bwd_fp (lists built once per label map) against
+    wesup_levels_pool_fwd/bwd (same weights rebuilt inside the kernels): equal up to fp32 summation order,
+    adjoint of each other, bit-reproducible, and rows beyond the true superpixel count pool to zero."""
+    from wesup_b200 import _lib
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    if kind == "grid":
+        seg = torch.from_numpy(synth.perturbed_grid_segments(h, w, max(2, int((h * w / n) ** 0.5)), seed=n)).long()
+    else:
+        seg = _scattered_segments(h, w, n, seed=n)
+    sp = SuperpixelMaps.from_labels(seg.to(DEV))
+    shifts = VGG_SHIFT if len(channels) == 13 else [0, 1, 3]
+    sides = [s.to(DEV).permute(0, 2, 3, 1).contiguous() for s in make_sides(h, w, seed=n, channels=channels, shifts=shifts)]
+    C, hs, ws_ = [s.size(3) for s in sides], [s.size(1) for s in sides], [s.size(2) for s in sides]
+    ca, ha, wa = _lib.int_array(C), _lib.int_array(hs), _lib.int_array(ws_)
+    ptrs = _lib.ptr_array([s.data_ptr() for s in sides])
+    ctot, nl = sum(C), len(C)
+    # fixed-capacity call: 5 extra rows with empty CSR segments, as the CUDA-graph iteration uses
+    cap = sp.n + 5
+    offs = torch.full((cap + 1,), h * w, dtype=torch.int32, device=DEV)
+    offs[:sp.n + 1] = sp.seg_offsets
+    counts = torch.zeros(cap, dtype=torch.int32, device=DEV)
+    counts[:sp.n] = sp.counts
+    nbytes = lib.wesup_footprint_bytes(ha, wa, nl, h, w, cap)
+    assert nbytes > 0
+    fp = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    _levels_call("wesup_footprint_build", ha, wa, nl, h, w, cap, offs.data_ptr(), sp.seg_pixels.data_ptr(),
+                 sp.row_labels.data_ptr(), counts.data_ptr(), 1, fp.data_ptr(), st)
+    a = torch.full((cap, ctot), float("nan"), device=DEV)
+    _levels_call("wesup_levels_pool_fwd_fp", ptrs, ca, ha, wa, nl, h, w, offs.data_ptr(), sp.seg_pixels.data_ptr(), cap,
+                 fp.data_ptr(), a.data_ptr(), st)
+    b = torch.empty(sp.n, ctot, device=DEV)
+    _levels_call("wesup_levels_pool_fwd", ptrs, ca, ha, wa, nl, h, w, sp.seg_offsets.data_ptr(), sp.seg_pixels.data_ptr(),
+                 sp.n, b.data_ptr(), st)
+    assert torch.isfinite(a).all() and float(a[sp.n:].abs().max()) == 0.0
+    tol = 1e-6 if h * w / sp.n < 2000 else 1e-5
+    assert rel_err(a[:sp.n], b) < tol
+    np.testing.assert_allclose(a[:sp.n].cpu().numpy(), b.cpu().numpy(), rtol=1e-5, atol=2e-6)
+    gp = torch.randn(cap, ctot, device=DEV)
+    ga = [torch.full_like(s, float("nan")) for s in sides]          # every element must be overwritten
+    gb = [torch.empty_like(s) for s in sides]
+    _levels_call("wesup_levels_pool_bwd_fp", gp.data_ptr(), sp.row_labels.data_ptr(), counts.data_ptr(), ca, ha, wa, nl, h, w, cap,
+                 fp.data_ptr(), _lib.ptr_array([t.data_ptr() for t in ga]), st)
+    wsl = torch.empty(lib.wesup_levels_pool_bwd_workspace_bytes(ca, ha, wa, nl, h, w), dtype=torch.uint8, device=DEV)
+    _levels_call("wesup_levels_pool_bwd", gp.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(), ca, ha, wa, nl, h, w,
+                 sp.n, _lib.ptr_array([t.data_ptr() for t in gb]), wsl.data_ptr(), st)
+    for x, y in zip(ga, gb):
+        assert torch.isfinite(x).all()
+        assert rel_err(x, y) < tol
+    lhs = (a.double() * gp.double()).sum()
+    rhs = sum((s_.double() * g.double()).sum() for s_, g in zip(sides, ga))
+    scale = float((a.double() * gp.double()).abs().sum())
+    assert abs(float(lhs - rhs)) < 1e-6 * scale + 1e-6
+    # a rebuilt blob may place its lists elsewhere (atomic cursor); the results must not change by a bit
+    fp2 = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    _levels_call("wesup_footprint_build", ha, wa, nl, h, w, cap, offs.data_ptr(), sp.seg_pixels.data_ptr(),
+                 sp.row_labels.data_ptr(), counts.data_ptr(), 1, fp2.data_ptr(), st)
+    a2 = torch.empty_like(a)
+    _levels_call("wesup_levels_pool_fwd_fp", ptrs, ca, ha, wa, nl, h, w, offs.data_ptr(), sp.seg_pixels.data_ptr(), cap,
+                 fp2.data_ptr(), a2.data_ptr(), st)
+    ga2 = [torch.empty_like(s) for s in sides]
+    _levels_call("wesup_levels_pool_bwd_fp", gp.data_ptr(), sp.row_labels.data_ptr(), counts.data_ptr(), ca, ha, wa, nl, h, w, cap,
+                 fp2.data_ptr(), _lib.ptr_array([t.data_ptr() for t in ga2]), st)
+    assert torch.equal(a, a2)
+    for x, y in zip(ga, ga2):
+        assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("h,w,n", [(37, 51, 7), (131, 97, 60), (464, 464, 1076)])
+def test_hypercolumn_pool_over_footprints_vs_dense_reference(h, w, n):
+    """`ops.hypercolumn_pool(..., footprints=build_footprints(...))` with the build forked onto a side
+    stream: forward and autograd gradients against the reference's dense formulation on the CPU."""
+    gen = torch.Generator().manual_seed(h * w + n)
+    sides = make_sides(h, w, seed=w)
+    seg = torch.from_numpy(synth.perturbed_grid_segments(h, w, max(2, int((h * w / n) ** 0.5)), seed=n)).long()
+    sp = SuperpixelMaps.from_labels(seg.to(DEV))
+    xs = [s.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for s in sides]
+    side_stream = torch.cuda.Stream()
+    fp = ops.build_footprints(sp, [(s.size(2), s.size(3)) for s in sides], with_bwd=True, stream=side_stream)
+    pooled, none = ops.hypercolumn_pool(xs, (h, w), sp, materialize=False, footprints=fp)
+    assert none is None
+    gp = torch.randn(pooled.shape, generator=gen)
+    pooled.backward(gp.to(DEV))
+    if h * w <= 20000:
+        maps, _, _ = O.preprocess_superpixels(seg, None)
+        ref_in = [s.clone().requires_grad_(True) for s in sides]
+        pooled_ref = O.pool_dense(maps, O.hypercolumn_from_sides(ref_in, (h, w)))
+        pooled_ref.backward(gp)
+        assert rel_err(pooled.cpu(), pooled_ref) < 1e-5
+        for x, r in zip(xs, ref_in):
+            assert rel_err(x.grad.cpu(), r.grad) < 1e-5
+    ys = [s.to(DEV).requires_grad_(True) for s in sides]
+    pooled_b, _ = ops.hypercolumn_pool(ys, (h, w), sp)                 # kernel (a) then kernel (b), fused backward
+    pooled_b.backward(gp.to(DEV))
+    assert rel_err(pooled, pooled_b) < 1e-6
+    for x, y in zip(xs, ys):
+        assert rel_err(x.grad, y.grad) < 1e-6
+    with pytest.raises(ValueError):
+        other = SuperpixelMaps.from_labels((seg // 2).to(DEV))
+        ops.hypercolumn_pool(xs, (h, w), other, materialize=False, footprints=fp)
+
+
 def test_fused_backward_full_size_adjoint_identity():
     """<pool(hyper(x)), g> == <x, fused_bwd(g)> at 464^2 with a SLIC-like grid of superpixels."""
     h = w = 464

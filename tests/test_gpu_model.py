@@ -33,12 +33,14 @@ def build(cls=WESUP, **kw):
     return model.to(DEV)
 
 
-@pytest.mark.parametrize("layout,fused,materialize,pool_first", [("hwc", True, True, False), ("hwc", False, True, False),
-                                                                ("chw", False, True, False), ("hwc", True, False, False),
-                                                                ("hwc", True, False, True)])
-def test_forward_loss_backward_matches_reference(golden, layout, fused, materialize, pool_first):
+@pytest.mark.parametrize("layout,fused,materialize,pool_first,footprints",
+                         [("hwc", True, True, False, True), ("hwc", False, True, False, True), ("chw", False, True, False, True),
+                          ("hwc", True, False, False, True), ("hwc", True, False, True, True),
+                          ("hwc", True, False, False, False), ("hwc", True, False, True, False)])
+def test_forward_loss_backward_matches_reference(golden, layout, fused, materialize, pool_first, footprints):
     g = golden("forward_loss_backward_48x40.npz")
-    model = build(hc_layout=layout, fused_backward=fused, materialize_hypercolumn=materialize, pool_first=pool_first)
+    model = build(hc_layout=layout, fused_backward=fused, materialize_hypercolumn=materialize, pool_first=pool_first,
+                  footprints=footprints)
     trainer = WESUPTrainer(model, device=DEV)
     x = synth.to_tensor(g["img_u8"]).unsqueeze(0).to(DEV)
     sp_maps, sp_labels = _preprocess_superpixels(torch.from_numpy(g["segments"]).to(DEV),

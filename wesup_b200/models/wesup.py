@@ -124,6 +124,10 @@ class WESUP(nn.Module):
                     convolutions then run on the N pooled rows instead of on H*W pixels -- a mean
                     and a 1x1 convolution commute, so `sp_features`/`sp_pred`/loss/gradients are the
                     reference's up to fp32 rounding (second half)
+      footprints    True (default; fused paths only): the aggregated bilinear weights of every
+                    superpixel (the sparse counterpart of the dense `sp_maps`) are built once per
+                    forward on a side stream while the backbone runs, and the pooling kernels
+                    stream over those lists.  False: the kernels rebuild them internally.
     """
 
     def __init__(self, n_classes=2, D=32, **kwargs):
@@ -149,6 +153,8 @@ class WESUP(nn.Module):
         self.fused_backward = bool(kwargs.get("fused_backward", True))
         self.materialize_hypercolumn = bool(kwargs.get("materialize_hypercolumn", True))
         self.pool_first = bool(kwargs.get("pool_first", True))
+        self.use_footprints = bool(kwargs.get("footprints", True))
+        self._fp_stream = None
         if self.hc_layout == "hwc":
             # the convolutions run channels_last: keep their weights (and therefore weight gradients
             # and momentum buffers) in that memory format too, so no per-iteration layout copies appear
@@ -179,10 +185,36 @@ class WESUP(nn.Module):
                 x = layer(x)
         return sides
 
+    def _level_sizes(self, height, width):
+        """(h, w) of every backbone conv output for an input of the given size (module arithmetic
+        only: known before the backbone runs)."""
+        def out(n, m):
+            k, st, p, d = (v if isinstance(v, int) else v[0] for v in (m.kernel_size, m.stride, m.padding, m.dilation))
+            return (n + 2 * p - d * (k - 1) - 1) // st + 1
+        sizes = []
+        for layer in self.backbone:
+            if isinstance(layer, nn.Conv2d):
+                height, width = out(height, layer), out(width, layer)
+                sizes.append((height, width))
+            elif isinstance(layer, nn.MaxPool2d):
+                height, width = out(height, layer), out(width, layer)
+        return sizes
+
+    def _start_footprints(self, x, sp):
+        """Fork the footprint build onto a side stream: it depends on the label map only and
+        overlaps the backbone; `ops.hypercolumn_pool` joins it."""
+        if not self.use_footprints:
+            return None
+        if self._fp_stream is None or self._fp_stream.device != x.device:
+            self._fp_stream = torch.cuda.Stream(device=x.device)
+        return ops.build_footprints(sp, self._level_sizes(x.size(2), x.size(3)), with_bwd=torch.is_grad_enabled(),
+                                    stream=self._fp_stream)
+
     def _pooled_first(self, x, sp):
         """Superpixel means of the PRE-ReLU backbone conv outputs (one fused kernel over the 13
         levels), then every side conv (reference :253, a 1x1 convolution + bias) as a small GEMM
         on the pooled rows: mean_S(W f + b) == W mean_S(f) + b."""
+        fp = self._start_footprints(x, sp)
         x = x.contiguous(memory_format=torch.channels_last)
         outs = []
         for layer in self.backbone:
@@ -193,7 +225,7 @@ class WESUP(nn.Module):
                 x = F.relu(x)            # out of place: the pooling kernel reads the pre-ReLU tensor afterwards
             else:
                 x = layer(x)
-        pooled, _ = ops.hypercolumn_pool(outs, self.fm_size, sp, materialize=False)
+        pooled, _ = ops.hypercolumn_pool(outs, self.fm_size, sp, materialize=False, footprints=fp)
         cols = []
         for name, part in zip(self._side_names, pooled.split([o.size(1) for o in outs], dim=1)):
             conv = getattr(self, name)
@@ -217,8 +249,9 @@ class WESUP(nn.Module):
             pooled = self._pooled_first(x, sp)
         elif self.fused_backward and self.hc_layout == "hwc":
             self.fm_size = (x.size(2), x.size(3))
+            fp = None if self.materialize_hypercolumn else self._start_footprints(x, sp)
             pooled, feats = ops.hypercolumn_pool(self._side_outputs(x), self.fm_size, sp, dtype=self.hc_dtype,
-                                                 materialize=self.materialize_hypercolumn)
+                                                 materialize=self.materialize_hypercolumn, footprints=fp)
             self.feature_maps = None if feats is None else feats.t().view(-1, *self.fm_size)
         else:
             feats = self._hypercolumn(x)

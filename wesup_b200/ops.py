@@ -191,6 +191,66 @@ class PendingSuperpixelMaps:
 
 
 # ---------------------------------------------------------------------------
+# precomputed pooling footprints (the sparse counterpart of the dense sp_maps)
+# ---------------------------------------------------------------------------
+class Footprints:
+    """Device blob written by `wesup_footprint_build` for one label map and one list of
+    level sizes: per superpixel the low-resolution cells it touches with their aggregated
+    bilinear weights (forward lists) and, `with_bwd`, the transpose per cell.  It plays the
+    role of the reference's `sp_maps` (/root/reference/models/wesup.py:57-61) for the fused
+    upsample + pooling operator and, like it, depends on the image only -- never on the
+    network weights -- so it is built once per image, off the critical path."""
+
+    def __init__(self, blob, hs, ws, height, width, n, with_bwd):
+        self.blob, self.hs, self.ws = blob, tuple(hs), tuple(ws)
+        self.height, self.width, self.n, self.with_bwd = int(height), int(width), int(n), bool(with_bwd)
+        self._pending: Optional[torch.cuda.Stream] = None
+
+    def matches(self, hs, ws, height, width, n) -> bool:
+        return (self.hs, self.ws, self.height, self.width, self.n) == (tuple(hs), tuple(ws), int(height), int(width), int(n))
+
+    def join(self) -> "Footprints":
+        """Make the current stream wait for a build that was forked onto a side stream."""
+        if self._pending is not None:
+            torch.cuda.current_stream(self.blob.device).wait_stream(self._pending)
+            self._pending = None
+        return self
+
+
+def build_footprints(sp: SuperpixelMaps, level_sizes: Sequence[Tuple[int, int]], with_bwd: bool = True,
+                     stream: Optional[torch.cuda.Stream] = None) -> Footprints:
+    """Build the pooling footprints of `sp` for feature levels of the given (h, w) sizes.
+    With `stream`, the build is forked from the current stream onto it (it then overlaps
+    whatever the caller enqueues next, e.g. the backbone) and `Footprints.join()` -- called by
+    `hypercolumn_pool` -- brings it back; the fork/join pair also captures into a CUDA graph."""
+    lib = _lib.load()
+    _require_cuda(sp.row_labels, "sp_maps")
+    hs, ws = [int(h) for h, _ in level_sizes], [int(w) for _, w in level_sizes]
+    ha, wa = _lib.int_array(hs), _lib.int_array(ws)
+    nbytes = lib.wesup_footprint_bytes(ha, wa, len(hs), sp.height, sp.width, sp.n)
+    if nbytes == 0:
+        raise ValueError(f"cannot plan pooling footprints for level sizes {list(zip(hs, ws))} on a {sp.height}x{sp.width} map")
+    dev = sp.row_labels.device
+    fp = Footprints(_ws(nbytes, dev), hs, ws, sp.height, sp.width, sp.n, with_bwd)
+
+    def launch():
+        check(lib.wesup_footprint_build(ha, wa, len(hs), sp.height, sp.width, sp.n, sp.seg_offsets.data_ptr(),
+                                        sp.seg_pixels.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
+                                        int(bool(with_bwd)), fp.blob.data_ptr(), _stream()), "wesup_footprint_build")
+
+    if stream is None:
+        launch()
+        return fp
+    stream.wait_stream(torch.cuda.current_stream(dev))
+    if not torch.cuda.is_current_stream_capturing():
+        fp.blob.record_stream(stream)
+    with torch.cuda.stream(stream):
+        launch()
+    fp._pending = stream
+    return fp
+
+
+# ---------------------------------------------------------------------------
 # (a) hypercolumn
 # ---------------------------------------------------------------------------
 def _as_hwc(t: torch.Tensor) -> torch.Tensor:
@@ -297,7 +357,7 @@ class _HypercolumnPool(torch.autograd.Function):
     of that size is kept for backward (both ops are linear)."""
 
     @staticmethod
-    def forward(ctx, sp: SuperpixelMaps, size, dtype, *sides):
+    def forward(ctx, sp: SuperpixelMaps, size, dtype, fp, *sides):
         lib = _lib.load()
         H, W = size
         for s in sides:
@@ -314,8 +374,17 @@ class _HypercolumnPool(torch.autograd.Function):
         dev = sides[0].device
         pooled = torch.empty((sp.n, ctot), dtype=torch.float32, device=dev)
         ptrs, ca, ha, wa = _lib.ptr_array([m.data_ptr() for m in mem]), _lib.int_array(C), _lib.int_array(h), _lib.int_array(w)
-        ctx.sp, ctx.geom = sp, (C, h, w, H, W)
-        if dtype is None:
+        if fp is not None and not fp.matches(h, w, H, W, sp.n):
+            raise ValueError("pooling footprints were built for another label map or other level sizes")
+        ctx.sp, ctx.geom, ctx.fp = sp, (C, h, w, H, W), fp
+        if dtype is None and fp is not None:
+            # fully fused over precomputed footprints: a prologue-free streaming gather
+            fp.join()
+            check(lib.wesup_levels_pool_fwd_fp(ptrs, ca, ha, wa, len(sides), H, W, sp.seg_offsets.data_ptr(),
+                                               sp.seg_pixels.data_ptr(), sp.n, fp.blob.data_ptr(), pooled.data_ptr(),
+                                               _stream()), "wesup_levels_pool_fwd_fp")
+            feats = torch.empty(0, dtype=torch.float32, device=dev)
+        elif dtype is None:
             # fully fused: superpixel means straight from the side outputs, no (H*W, C) tensor
             check(lib.wesup_hypercolumn_pool_fwd(ptrs, ca, ha, wa, len(sides), H, W, sp.seg_offsets.data_ptr(),
                                                  sp.seg_pixels.data_ptr(), sp.n, pooled.data_ptr(), _stream()),
@@ -340,22 +409,32 @@ class _HypercolumnPool(torch.autograd.Function):
         dev = grad_pooled.device
         mem = [torch.empty((1, hh, ww, cc), dtype=torch.float32, device=dev) for cc, hh, ww in zip(C, h, w)]
         ca, ha, wa = _lib.int_array(C), _lib.int_array(h), _lib.int_array(w)
-        ws = _ws(lib.wesup_sp_pool_hypercolumn_bwd_workspace_bytes(ca, ha, wa, len(C), H, W, sp.n), dev)
-        check(lib.wesup_sp_pool_hypercolumn_bwd(grad_pooled.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
-                                                ca, ha, wa, len(C), H, W, sp.n,
-                                                _lib.ptr_array([m.data_ptr() for m in mem]), ws.data_ptr(), _stream()),
-              "wesup_sp_pool_hypercolumn_bwd")
-        return (None, None, None, *[m.permute(0, 3, 1, 2) for m in mem])
+        fp = ctx.fp
+        if fp is not None and fp.with_bwd:
+            fp.join()
+            check(lib.wesup_levels_pool_bwd_fp(grad_pooled.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
+                                               ca, ha, wa, len(C), H, W, sp.n, fp.blob.data_ptr(),
+                                               _lib.ptr_array([m.data_ptr() for m in mem]), _stream()),
+                  "wesup_levels_pool_bwd_fp")
+        else:
+            ws = _ws(lib.wesup_sp_pool_hypercolumn_bwd_workspace_bytes(ca, ha, wa, len(C), H, W, sp.n), dev)
+            check(lib.wesup_sp_pool_hypercolumn_bwd(grad_pooled.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
+                                                    ca, ha, wa, len(C), H, W, sp.n,
+                                                    _lib.ptr_array([m.data_ptr() for m in mem]), ws.data_ptr(), _stream()),
+                  "wesup_sp_pool_hypercolumn_bwd")
+        return (None, None, None, None, *[m.permute(0, 3, 1, 2) for m in mem])
 
 
 def hypercolumn_pool(sides: Sequence[torch.Tensor], size: Tuple[int, int], sp: SuperpixelMaps, dtype=torch.float32,
-                     materialize: bool = True):
+                     materialize: bool = True, footprints: Optional[Footprints] = None):
     """Hypercolumn (a) + superpixel mean pooling (b) with the fused backward.
     Returns (pooled (N,C) fp32, feats).  materialize=True (default): `feats` is the
     (H*W,C) `dtype` hypercolumn written by kernel (a) (non-differentiable output).
     materialize=False: one fused forward kernel pools straight from the side outputs,
-    `feats` is None and nothing of size H*W*C is ever allocated."""
-    pooled, feats = _HypercolumnPool.apply(sp, (int(size[0]), int(size[1])), dtype if materialize else None, *sides)
+    `feats` is None and nothing of size H*W*C is ever allocated; with `footprints`
+    (`build_footprints`) the forward and the backward stream over the precomputed lists."""
+    pooled, feats = _HypercolumnPool.apply(sp, (int(size[0]), int(size[1])), dtype if materialize else None, footprints,
+                                           *sides)
     return pooled, (feats if materialize else None)
 
 
