@@ -28,6 +28,35 @@ __global__ void __launch_bounds__(512) read_kernel(const float4 *__restrict__ p,
     if (acc.x == 1234.5f) out[0] = acc;
 }
 
+// HBM gather: every warp reads whole chunks of `chunk` bytes at pseudo-random chunk-aligned offsets of a 1 GB buffer
+// (four 512-byte warp loads in flight).  chunk = 128 KB behaves like a stream; a few KB is what the footprint gathers
+// issue (one bounding-box row of cells of one level: 3.5 - 8 KB).
+__global__ void __launch_bounds__(256) gather_kernel(const float4 *__restrict__ p, size_t n_chunks_buf, int chunk_f4, size_t n_chunks_read,
+                                                     float4 *out) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t c = warp; c < n_chunks_read; c += n_warps) {
+        const size_t h = (c * 0x9E3779B97F4A7C15ull) >> 20;
+        const float4 *src = p + (h % n_chunks_buf) * (size_t)chunk_f4;
+        int i = lane;
+        for (; i + 96 < chunk_f4; i += 128) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(src + i + 32 * u));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        }
+        for (; i < chunk_f4; i += 32) {
+            float4 v;
+            asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + i));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    if (acc.x == 1234.5f) out[0] = acc;
+}
+
 int main() {
     const size_t max_bytes = (size_t)1 << 30;
     float4 *buf, *out;
@@ -48,6 +77,19 @@ int main() {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, a, b);
         printf("%s\"read_%dMB_gbs\": %.1f", t ? ", " : "", mbs[t], (double)bytes * reps / ms / 1e6);
+    }
+    const int chunks[] = {512, 1024, 2048, 4096, 8192, 32768, 131072};
+    for (int t = 0; t < 7; ++t) {
+        const int chunk_f4 = chunks[t] / 16;
+        const size_t n_buf = max_bytes / chunks[t], n_read = ((size_t)512 << 20) / chunks[t];
+        gather_kernel<<<148 * 8, 256>>>(buf, n_buf, chunk_f4, n_read / 8, out);
+        cudaEventRecord(a);
+        gather_kernel<<<148 * 8, 256>>>(buf, n_buf, chunk_f4, n_read, out);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        printf(", \"gather_%dB_gbs\": %.1f", chunks[t], (double)n_read * chunks[t] / ms / 1e6);
     }
     printf("}\n");
     return cudaGetLastError() != cudaSuccess;
