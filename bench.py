@@ -147,9 +147,25 @@ def run_reference(args):
 QUICK = bool(int(os.environ.get("WESUP_BENCH_QUICK", "0")))     # 1 launch per kernel (ncu --set full captures)
 
 
+class L2Flush:
+    """Evicts the 126 MB L2 between timed launches: a 256 MB write, then a 256 MB read of a second
+    buffer.  The write alone would leave ~126 MB of DIRTY lines behind, whose write-back would then
+    be charged (as extra DRAM traffic, ~20 us) to whatever kernel is timed next; the read pass forces
+    that write-back before the timed region and leaves clean lines."""
+
+    def __init__(self, dev, nbytes=256 << 20):
+        import torch
+        self.w = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.r = torch.zeros(nbytes // 4, dtype=torch.int32, device=dev)
+
+    def __call__(self):
+        self.w.zero_()
+        self.r.sum()
+
+
 def time_kernel(fn, iters, flush):
     """Average device time of `fn` in ms over `iters` launches, CUDA events on the
-    current stream, an L2 flush (write of a > L2 buffer) before every launch."""
+    current stream, an L2 flush (`L2Flush`) before every launch."""
     import torch
     if QUICK:
         iters = 1
@@ -158,7 +174,7 @@ def time_kernel(fn, iters, flush):
     torch.cuda.synchronize()
     total = 0.0
     for _ in range(iters):
-        flush.zero_()
+        flush()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         fn()
@@ -174,7 +190,7 @@ def kernel_rooflines(dev, peak_gbs):
     import torch
     from wesup_b200 import ops, synth
     from wesup_b200.ops import SuperpixelMaps
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = L2Flush(dev)
     g = torch.Generator(device="cpu").manual_seed(0)
     sides = [torch.randn(1, c, H >> s, W >> s, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
              for c, s in zip(VGG_C, VGG_SHIFT)]
@@ -439,7 +455,7 @@ def run_own(args):
                        "precomputed per image (wesup_footprint_build, forked beside the backbone)",
                        "iteration": "eager" if args.no_graph else "one CUDA graph per image shape (SLIC .. SGD step), replayed",
                        "parallelism": f"dp{world}", "l2": "working set 1.8 GB/image (hypercolumn) >> 126 MB L2; "
-                       "kernel microbenches flush L2 with a 256 MB write before every launch",
+                       "kernel microbenches flush L2 (256 MB write, then 256 MB read so no dirty lines remain) before every launch",
                        "cudnn_tf32": bool(torch.backends.cudnn.allow_tf32)},
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d * ips, "d2h_bytes_per_step": 4 * ips,
                     "ms_per_step": ms_e2e / args.steps},

@@ -397,6 +397,17 @@ def test_precomputed_footprint_pooling_matches_the_in_kernel_footprint_kernels(h
     assert torch.isfinite(a).all() and float(a[sp.n:].abs().max()) == 0.0
     tol = 1e-6 if h * w / sp.n < 2000 else 1e-5
     assert rel_err(a[:sp.n], b) < tol
+    # the library has two forward kernels over the lists (whole cells per warp for 32..512-channel levels, 128-channel
+    # chunks otherwise); WESUP_FP_FWD=chunks forces the second one: same sums in another order
+    import os
+    os.environ["WESUP_FP_FWD"] = "chunks"
+    try:
+        a_chunks = torch.full((cap, ctot), float("nan"), device=DEV)
+        _levels_call("wesup_levels_pool_fwd_fp", ptrs, ca, ha, wa, nl, h, w, offs.data_ptr(), sp.seg_pixels.data_ptr(), cap,
+                     fp.data_ptr(), a_chunks.data_ptr(), st)
+    finally:
+        os.environ.pop("WESUP_FP_FWD")
+    assert torch.isfinite(a_chunks).all() and rel_err(a_chunks, a) < tol
     np.testing.assert_allclose(a[:sp.n].cpu().numpy(), b.cpu().numpy(), rtol=1e-5, atol=2e-6)
     gp = torch.randn(cap, ctot, device=DEV)
     ga = [torch.full_like(s, float("nan")) for s in sides]          # every element must be overwritten

@@ -15,7 +15,7 @@ if __name__ == "__main__":
     H = int(sys.argv[1]) if len(sys.argv) > 1 else 464
     W = int(sys.argv[2]) if len(sys.argv) > 2 else H
     dev = torch.device("cuda", 0)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = bench.L2Flush(dev)
     g = torch.Generator().manual_seed(0)
     sides = [torch.randn(1, c, H >> s, W >> s, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
              for c, s in zip(bench.VGG_C, bench.VGG_SHIFT)]

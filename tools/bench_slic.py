@@ -23,7 +23,7 @@ if __name__ == "__main__":
     n = torch.zeros(1, dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     fn = lambda: ops.check(lib.wesup_slic(x.data_ptr(), 0, H, W, n_seg, 40.0, 10, 1, labels.data_ptr(), n.data_ptr(), ws.data_ptr(), st), "slic")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = bench.L2Flush(dev)
     ms = bench.time_kernel(fn, reps, flush)
     # back-to-back (no flush, launch-overhead hidden by queueing)
     torch.cuda.synchronize()

@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace wesup {
 
@@ -559,6 +560,105 @@ __global__ void __launch_bounds__(FP_THREADS, 4) fp_pool_fwd_kernel(const Levels
     }
 }
 
+// fwd, whole cells (default): a warp owns (superpixel k, LEVEL l) and reads every listed cell of the level in
+// full -- C_l * 4 contiguous bytes: V = C_l / 128 consecutive 128-bit loads per lane, or, for C_l = 64 / 32, EPS = 2 / 4
+// consecutive entries side by side in one warp load -- so that the loads a warp has in flight cover 2 - 4 KB of
+// contiguous memory (a run of cells of one bounding-box row), not eight scattered 512-byte pieces: tools/l2bw.cu
+// measures 6.0 - 6.6 TB/s for gathers of 2 - 4 KB pieces against 2.3 TB/s for 512-byte ones.  The list lives in
+// registers, one entry per lane (blocks of 32), index and weight broadcast with shuffles; eight loads per lane in
+// flight; no shared memory, no barrier, 64-thread blocks so that a finished warp frees its slot early.
+constexpr int FC_THREADS = 64;
+constexpr int FC_WARPS = FC_THREADS / 32;
+constexpr int FC_INFLIGHT = 8;
+
+template <int V, int EPS>
+__device__ __forceinline__ void fc_unit(const float *__restrict__ level, int Cl, const int32_t *__restrict__ px, const FpEnt *__restrict__ ent,
+                                        int ne, float inv, float *__restrict__ out, int lane) {
+    constexpr int UF = FC_INFLIGHT / V;                     // entry slots per batch
+    constexpr int LPE = 32 / EPS;                           // lanes per entry
+    const int sub = lane / LPE;                             // which entry of a slot this lane reads
+    const float *__restrict__ src = level + (lane - sub * LPE) * 4;
+    float4 acc[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e0 = 0; e0 < ne; e0 += 32) {
+        const int eg = e0 + lane;
+        const bool valid = eg < ne;
+        const int ee = valid ? eg : e0;                     // the tail repeats entry e0 with weight 0
+        int my_idx;
+        float my_w;
+        if (px) { my_idx = __ldg(px + ee); my_w = valid ? 1.0f : 0.f; }
+        else { const FpEnt a = ld_ent(ent + ee); my_idx = a.idx; my_w = valid ? a.w : 0.f; }
+        const int nb = min(32, ne - e0);
+        for (int e = 0; e < nb; e += UF * EPS) {            // padded batches: slots past the list carry weight 0 and a valid index
+            float4 v[UF][V];
+            float wv[UF];
+#pragma unroll
+            for (int u = 0; u < UF; ++u) {
+                const int slot = e + u * EPS + sub;
+                const int idx = __shfl_sync(0xffffffffu, my_idx, slot & 31);
+                const float ws = __shfl_sync(0xffffffffu, my_w, slot & 31);
+                wv[u] = slot < 32 ? ws : 0.f;
+                const float4 *row = reinterpret_cast<const float4 *>(src + (long)idx * Cl);
+#pragma unroll
+                for (int q = 0; q < V; ++q) v[u][q] = __ldg(row + 32 * q);
+            }
+#pragma unroll
+            for (int u = 0; u < UF; ++u)
+#pragma unroll
+                for (int q = 0; q < V; ++q) fma4(acc[q], wv[u], v[u][q]);
+        }
+    }
+    if (EPS > 1) {                                          // fold the entry groups of the warp (fixed order)
+#pragma unroll
+        for (int o = 16; o >= LPE; o >>= 1) {
+            acc[0].x += __shfl_down_sync(0xffffffffu, acc[0].x, o);
+            acc[0].y += __shfl_down_sync(0xffffffffu, acc[0].y, o);
+            acc[0].z += __shfl_down_sync(0xffffffffu, acc[0].z, o);
+            acc[0].w += __shfl_down_sync(0xffffffffu, acc[0].w, o);
+        }
+        if (lane < LPE) *reinterpret_cast<float4 *>(out + lane * 4) = inv * acc[0];
+    } else {
+#pragma unroll
+        for (int q = 0; q < V; ++q) *reinterpret_cast<float4 *>(out + q * 128 + lane * 4) = inv * acc[q];
+    }
+}
+
+// levels of 32, 64, 128, 256 or 512 channels (host-checked); units are level-major, so blocks are level-homogeneous
+__global__ void __launch_bounds__(FC_THREADS, 12) fp_pool_fwd_cells_kernel(const Levels L, const FpPlan P, const PoolPlan F,
+                                                                           const int32_t *__restrict__ seg_offsets,
+                                                                           const int32_t *__restrict__ seg_pixels, int N,
+                                                                           float *__restrict__ pooled) {
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bpl = (N + FC_WARPS - 1) / FC_WARPS;          // blocks per level
+    const int l = (int)blockIdx.x / bpl;
+    const int k = ((int)blockIdx.x - l * bpl) * FC_WARPS + wid;
+    if (k >= N) return;
+    int g = 0;
+    while (g + 1 < F.n && l >= F.g[g + 1].l0) ++g;
+    const int res = F.g[g].res;
+    const int beg = __ldg(seg_offsets + k), n_px = __ldg(seg_offsets + k + 1) - beg;
+    const int32_t *__restrict__ px = nullptr;
+    const FpEnt *__restrict__ ent = nullptr;
+    int ne = n_px;
+    if (res < 0) {
+        px = seg_pixels + beg;
+    } else {
+        const int2 span = __ldg(P.r[res].fwd_span + k);     // an empty superpixel has an empty list
+        ent = P.r[res].fwd_ent + span.x;
+        ne = span.y;
+    }
+    const float inv = n_px > 0 ? 1.0f / (float)n_px : 0.f;
+    float *__restrict__ out = pooled + (long)k * L.Ctot + L.coff[l];
+    const int Cl = L.C[l];
+    const float *__restrict__ level = L.src[l];
+    if (Cl == 512) fc_unit<4, 1>(level, Cl, px, ent, ne, inv, out, lane);
+    else if (Cl == 256) fc_unit<2, 1>(level, Cl, px, ent, ne, inv, out, lane);
+    else if (Cl == 128) fc_unit<1, 1>(level, Cl, px, ent, ne, inv, out, lane);
+    else if (Cl == 64) fc_unit<1, 2>(level, Cl, px, ent, ne, inv, out, lane);
+    else fc_unit<1, 4>(level, Cl, px, ent, ne, inv, out, lane);
+}
+
 // bwd: unit = (low-resolution cell q, group, 256-channel slice), one warp per unit, two float4 per lane;
 // the pooled-gradient rows (N x Ctot, L2-resident) of four list entries are in flight together.
 template <int U>
@@ -795,6 +895,17 @@ extern "C" int wesup_levels_pool_fwd_fp(const void *const *level, const int *C, 
         G.split = expect >= 8.0 * per_warp ? 8 : expect >= 4.0 * per_warp ? 4 : expect >= 2.0 * per_warp ? 2 : 1;
         G.blk0 = blocks;
         blocks += cdiv((long)N * G.nchunk, FP_WARPS / G.split);
+    }
+    // default: whole cells per warp (levels of 32 .. 512 channels); any other channel count takes the chunk kernel,
+    // which WESUP_FP_FWD=chunks also selects (cross-check in the tests)
+    bool cells = getenv("WESUP_FP_FWD") == nullptr;
+    for (int l = 0; l < L.n; ++l) cells = cells && (L.C[l] == 32 || L.C[l] == 64 || L.C[l] == 128 || L.C[l] == 256 || L.C[l] == 512);
+    if (cells) {
+        const long cb = (long)L.n * cdiv(N, FC_WARPS);
+        WESUP_REQUIRE(cb < (1L << 31), WESUP_E_UNSUPPORTED, "wesup_levels_pool_fwd_fp: problem too large");
+        fp_pool_fwd_cells_kernel<<<(int)cb, FC_THREADS, 0, stream>>>(L, P, F, seg_offsets, seg_pixels, N, pooled);
+        WESUP_CHECK_LAUNCH("wesup_levels_pool_fwd_fp", 1);
+        return 0;
     }
     WESUP_REQUIRE(blocks >= 0 && (long)blocks * FP_WARPS < (1L << 31), WESUP_E_UNSUPPORTED, "wesup_levels_pool_fwd_fp: problem too large");
     fp_pool_fwd_kernel<8><<<blocks, FP_THREADS, 0, stream>>>(L, P, F, seg_offsets, seg_pixels, N, pooled);
