@@ -418,9 +418,9 @@ def run_own(args):
             else:
                 key = max((f"fp_pool_fwd_{tag}", f"fp_pool_bwd_{tag}"), key=lambda k_: kernels[k_]["ms"])
                 if "fwd" in key:
-                    name, label = "fp_pool_fwd_kernel", "fp_pool_fwd_kernel (wesup_levels_pool_fwd_fp)"
+                    name, label = "fp_pool_fwd_cells_kernel", "fp_pool_fwd_cells_kernel (wesup_levels_pool_fwd_fp)"
                 else:
-                    name, label = "fp_pool_bwd", "fp_pool_bwd_kernel + fp_pool_bwd_ident_kernel (wesup_levels_pool_bwd_fp)"
+                    name, label = "fp_pool_bwd", "fp_pool_bwd_cells_kernel + fp_pool_bwd_ident_kernel, concurrent (wesup_levels_pool_bwd_fp)"
         k = kernels[key]
         traffic = None
         tfile = ROOT / "profiles" / "roofline_traffic.json"

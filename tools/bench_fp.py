@@ -53,6 +53,9 @@ def main():
         os.environ["WESUP_FP_FWD"] = "chunks"
         out["fwd_chunk_kernel"] = timed(fwd)
         os.environ.pop("WESUP_FP_FWD")
+        os.environ["WESUP_FP_BWD"] = "chunks"
+        out["bwd_chunk_kernel"] = timed(bwd)
+        os.environ.pop("WESUP_FP_BWD")
     print(json.dumps(out))
 
 

@@ -716,6 +716,141 @@ __global__ void __launch_bounds__(FP_THREADS) fp_pool_bwd_kernel(const Levels L,
     }
 }
 
+// bwd, whole cells (default for levels of 128 / 256 / 512 channels): a warp writes complete cell rows of ONE level
+// (C_l * 4 contiguous bytes, V = C_l / 128 float4 per lane) and keeps the lists in registers.
+//   * short lists (fine levels: a 4x4 / 8x8 footprint meets 1 - 3 superpixels): the warp takes 32 CONSECUTIVE cells;
+//     lane i loads the span and the first EPRE entries of cell q0 + i -- one round of coalesced loads for 32 cells
+//     instead of a span -> entries chain per cell -- and the cells are then walked CU at a time with their
+//     pooled-gradient rows (L2-resident) in flight together; entries beyond EPRE take a plain loop;
+//   * long lists (coarse levels): one cell per warp, the list one entry per lane, broadcast with shuffles,
+//     8 / V entries in flight -- the forward kernel transposed.
+constexpr int BC_THREADS = 128;
+constexpr int BC_WARPS = BC_THREADS / 32;
+struct BwdCellsPlan {
+    int n;                               // levels handled here
+    int lvl[WESUP_MAX_LEVELS], res[WESUP_MAX_LEVELS], batch[WESUP_MAX_LEVELS], blk0[WESUP_MAX_LEVELS + 1];
+};
+
+template <int V, int EPRE, int CU>
+__device__ __forceinline__ void bc_batch(const float *__restrict__ gpl, int Ctot, float *__restrict__ dst, int Cl, const FpRes &R,
+                                         int q0, int cells, int lane) {
+    const int q = q0 + lane;
+    const int2 span = q < cells ? __ldg(R.bwd_span + q) : make_int2(0, 0);
+    FpEnt pre[EPRE];
+#pragma unroll
+    for (int u = 0; u < EPRE; ++u) {
+        pre[u].idx = 0; pre[u].w = 0.f;                     // row 0 with weight 0: a valid address, no contribution
+        if (u < span.y) pre[u] = ld_ent(R.bwd_ent + span.x + u);
+    }
+    const int nc = min(32, cells - q0);
+    for (int c0 = 0; c0 < nc; c0 += CU) {
+        float4 v[CU][EPRE][V];
+        float wv[CU][EPRE];
+        int n_c[CU];
+#pragma unroll
+        for (int t = 0; t < CU; ++t) {
+            const int c = min(c0 + t, nc - 1);              // the last group may repeat its last cell (stores are guarded)
+            n_c[t] = __shfl_sync(0xffffffffu, span.y, c);
+#pragma unroll
+            for (int u = 0; u < EPRE; ++u) {
+                const int k = __shfl_sync(0xffffffffu, pre[u].idx, c);
+                wv[t][u] = __shfl_sync(0xffffffffu, pre[u].w, c);
+                const float4 *row = reinterpret_cast<const float4 *>(gpl + (long)k * Ctot);
+#pragma unroll
+                for (int qv = 0; qv < V; ++qv) v[t][u][qv] = __ldg(row + 32 * qv);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < CU; ++t) {
+            if (c0 + t >= nc) break;                        // warp-uniform
+            float4 acc[V];
+#pragma unroll
+            for (int qv = 0; qv < V; ++qv) acc[qv] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < EPRE; ++u)
+#pragma unroll
+                for (int qv = 0; qv < V; ++qv) fma4(acc[qv], wv[t][u], v[t][u][qv]);
+            if (n_c[t] > EPRE) {                            // warp-uniform: the rest of a long list
+                const int base = __shfl_sync(0xffffffffu, span.x, c0 + t);
+                for (int e = EPRE; e < n_c[t]; ++e) {
+                    const FpEnt a = ld_ent(R.bwd_ent + base + e);
+                    const float4 *row = reinterpret_cast<const float4 *>(gpl + (long)a.idx * Ctot);
+#pragma unroll
+                    for (int qv = 0; qv < V; ++qv) fma4(acc[qv], a.w, __ldg(row + 32 * qv));
+                }
+            }
+            float4 *o = reinterpret_cast<float4 *>(dst + (long)(q0 + c0 + t) * Cl);
+#pragma unroll
+            for (int qv = 0; qv < V; ++qv) stg_stream(o + 32 * qv, acc[qv]);
+        }
+    }
+}
+
+template <int V>
+__device__ __forceinline__ void bc_cell(const float *__restrict__ gpl, int Ctot, float *__restrict__ dst, int Cl, const FpRes &R, int q,
+                                        int lane) {
+    constexpr int UF = 8 / V;
+    const int2 span = __ldg(R.bwd_span + q);
+    const FpEnt *__restrict__ ent = R.bwd_ent + span.x;
+    const int ne = span.y;
+    float4 acc[V];
+#pragma unroll
+    for (int qv = 0; qv < V; ++qv) acc[qv] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e0 = 0; e0 < ne; e0 += 32) {
+        const int eg = e0 + lane;
+        const bool valid = eg < ne;
+        const FpEnt mine = ld_ent(ent + (valid ? eg : e0));  // the tail repeats entry e0 with weight 0
+        const float my_w = valid ? mine.w : 0.f;
+        const int nb = min(32, ne - e0);
+        for (int e = 0; e < nb; e += UF) {                  // padded batches
+            float4 v[UF][V];
+            float wv[UF];
+#pragma unroll
+            for (int u = 0; u < UF; ++u) {
+                const int k = __shfl_sync(0xffffffffu, mine.idx, (e + u) & 31);
+                const float ws = __shfl_sync(0xffffffffu, my_w, (e + u) & 31);
+                wv[u] = e + u < 32 ? ws : 0.f;
+                const float4 *row = reinterpret_cast<const float4 *>(gpl + (long)k * Ctot);
+#pragma unroll
+                for (int qv = 0; qv < V; ++qv) v[u][qv] = __ldg(row + 32 * qv);
+            }
+#pragma unroll
+            for (int u = 0; u < UF; ++u)
+#pragma unroll
+                for (int qv = 0; qv < V; ++qv) fma4(acc[qv], wv[u], v[u][qv]);
+        }
+    }
+    float4 *o = reinterpret_cast<float4 *>(dst + (long)q * Cl);
+#pragma unroll
+    for (int qv = 0; qv < V; ++qv) stg_stream(o + 32 * qv, acc[qv]);
+}
+
+__global__ void __launch_bounds__(BC_THREADS, 6) fp_pool_bwd_cells_kernel(const Levels L, const FpPlan P, const BwdCellsPlan B,
+                                                                          const float *__restrict__ gp) {
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int i = 0;
+    while (i + 1 < B.n && (int)blockIdx.x >= B.blk0[i + 1]) ++i;
+    const int l = B.lvl[i];
+    const FpRes &R = P.r[B.res[i]];
+    const int cells = R.h * R.w;
+    const int Cl = L.C[l], Ctot = L.Ctot;
+    const float *__restrict__ gpl = gp + L.coff[l] + lane * 4;
+    float *__restrict__ dst = L.dst[l] + lane * 4;
+    const int wunit = ((int)blockIdx.x - B.blk0[i]) * BC_WARPS + wid;
+    if (B.batch[i]) {
+        const int q0 = wunit * 32;
+        if (q0 >= cells) return;
+        if (Cl == 128) bc_batch<1, 2, 4>(gpl, Ctot, dst, Cl, R, q0, cells, lane);
+        else if (Cl == 256) bc_batch<2, 2, 2>(gpl, Ctot, dst, Cl, R, q0, cells, lane);
+        else bc_batch<4, 2, 1>(gpl, Ctot, dst, Cl, R, q0, cells, lane);
+    } else {
+        if (wunit >= cells) return;
+        if (Cl == 128) bc_cell<1>(gpl, Ctot, dst, Cl, R, wunit, lane);
+        else if (Cl == 256) bc_cell<2>(gpl, Ctot, dst, Cl, R, wunit, lane);
+        else bc_cell<4>(gpl, Ctot, dst, Cl, R, wunit, lane);
+    }
+}
+
 // full-resolution levels: grad[p, c] = grad_pooled[row(p), c] / |S_row(p)|; four pixels per thread so that
 // the label -> count -> row chain of four pixels is in flight together
 __global__ void __launch_bounds__(256) fp_pool_bwd_ident_kernel(const Levels L, const PoolGroup bg, const float *__restrict__ gp,
@@ -928,12 +1063,40 @@ extern "C" int wesup_levels_pool_bwd_fp(const float *grad_pooled, const int32_t 
                   "wesup_levels_pool_bwd_fp: more than %d distinct level resolutions", FP_MAX_RES);
     PoolPlan G;
     WESUP_REQUIRE(build_pool_groups(G, L, P) == 0, WESUP_E_ARG, "wesup_levels_pool_bwd_fp: level resolution missing from the footprint plan");
-    // non-identity groups in ONE launch, coarse (longest lists) first; identity groups stream separately
+    // non-identity levels of 128 / 256 / 512 channels: whole cells per warp, coarse levels (long lists) first; a group
+    // with any other channel count (and WESUP_FP_BWD=chunks, the cross-check of the tests) takes the chunk kernel
+    const double side = sqrt((double)H * W / (double)N);
+    const bool force_chunks = getenv("WESUP_FP_BWD") != nullptr;
+    BwdCellsPlan BC;
+    BC.n = 0;
+    long cblocks = 0;
+    bool group_cells[WESUP_MAX_LEVELS];
+    for (int g = G.n - 1; g >= 0; --g) {
+        group_cells[g] = false;
+        if (G.g[g].res < 0) continue;
+        bool ok = !force_chunks;
+        for (int l = G.g[g].l0; l < G.g[g].l1; ++l) ok = ok && (L.C[l] == 128 || L.C[l] == 256 || L.C[l] == 512);
+        group_cells[g] = ok;
+        if (!ok) continue;
+        const FpRes &R = P.r[G.g[g].res];
+        // superpixels met by a cell's footprint (2/scale pixels wide): short lists take the 32-cells-per-warp path
+        const double fy = R.sy > 0.f ? 2.0 / R.sy : (double)H, fx = R.sx > 0.f ? 2.0 / R.sx : (double)W;
+        const bool batch = (fy / side + 1.0) * (fx / side + 1.0) < 3.5;
+        for (int l = G.g[g].l0; l < G.g[g].l1; ++l) {
+            const int i = BC.n++;
+            BC.lvl[i] = l; BC.res[i] = G.g[g].res; BC.batch[i] = batch ? 1 : 0;
+            BC.blk0[i] = (int)cblocks;
+            const long cells = (long)R.h * R.w;
+            cblocks += cdiv(batch ? cdiv(cells, 32) : cells, BC_WARPS);
+        }
+    }
+    BC.blk0[BC.n] = (int)cblocks;
+    WESUP_REQUIRE(cblocks < (1L << 28), WESUP_E_UNSUPPORTED, "wesup_levels_pool_bwd_fp: problem too large");
     PoolPlan B;
     B.n = 0;
     int blocks = 0, launched = 0;
     for (int g = G.n - 1; g >= 0; --g) {
-        if (G.g[g].res < 0) continue;
+        if (G.g[g].res < 0 || group_cells[g]) continue;
         PoolGroup &S = B.g[B.n++];
         S = G.g[g];
         S.nchunk = (S.Cg + 255) / 256;
@@ -945,9 +1108,13 @@ extern "C" int wesup_levels_pool_bwd_fp(const float *grad_pooled, const int32_t 
     bool any_ident = false;
     for (int g = 0; g < G.n; ++g) any_ident = any_ident || G.g[g].res < 0;
     cudaStream_t s_ident = stream;
-    AuxStream *aux = (B.n > 0 && any_ident) ? aux_stream() : nullptr;
+    AuxStream *aux = ((B.n > 0 || BC.n > 0) && any_ident) ? aux_stream() : nullptr;
     if (aux && cudaEventRecord(aux->fork, stream) == cudaSuccess && cudaStreamWaitEvent(aux->s, aux->fork, 0) == cudaSuccess)
         s_ident = aux->s;
+    if (BC.n > 0) {
+        fp_pool_bwd_cells_kernel<<<(int)cblocks, BC_THREADS, 0, stream>>>(L, P, BC, grad_pooled);
+        ++launched;
+    }
     if (B.n > 0) {
         fp_pool_bwd_kernel<2><<<blocks, FP_THREADS, 0, stream>>>(L, P, B, grad_pooled);
         ++launched;
