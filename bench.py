@@ -420,13 +420,14 @@ def run_own(args):
                 if "fwd" in key:
                     name, label = "fp_pool_fwd_cells_kernel", "fp_pool_fwd_cells_kernel (wesup_levels_pool_fwd_fp)"
                 else:
-                    name, label = "fp_pool_bwd", "fp_pool_bwd_cells_kernel + fp_pool_bwd_ident_kernel, concurrent (wesup_levels_pool_bwd_fp)"
+                    name, label = "fp_pool_bwd_cells_kernel|fp_pool_bwd_ident_kernel", "fp_pool_bwd_cells_kernel + fp_pool_bwd_ident_kernel, concurrent (wesup_levels_pool_bwd_fp)"
         k = kernels[key]
         traffic = None
         tfile = ROOT / "profiles" / "roofline_traffic.json"
         if tfile.exists():
             tj = json.loads(tfile.read_text())
-            hits = [v["traffic_bytes"] for n_, v in tj.items() if isinstance(v, dict) and name.split("(")[0] in n_]
+            wanted = [n_.split("(")[0] for n_ in name.split("|")]
+            hits = [v["traffic_bytes"] for n_, v in tj.items() if isinstance(v, dict) and any(w_ in n_ for w_ in wanted)]
             traffic = sum(hits) if hits else None
         roofline = {"kernel": label, "bound": "hbm", "achieved": k["gbs"],
                     "peak": peak, "peak_source": peak_src + ": a read+write copy; write-only streams measure 7.4 TB/s on this pool",

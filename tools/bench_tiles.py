@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--mode", choices=["sp", "pixel"], default="sp")
     ap.add_argument("--hc-dtype", choices=["fp32", "bf16"], default="fp32")
     ap.add_argument("--no-graph", action="store_true", help="eager tile steps (default: CUDA graphs)")
+    ap.add_argument("--no-footprints", action="store_true", help="sp mode: pooling kernels rebuild the footprints internally")
     ap.add_argument("--materialize", action="store_true", help="sp mode: write the (H*W,2112) hypercolumn, then pool it")
     args = ap.parse_args()
     rank, world, local = parallel.init_from_env("nccl")
@@ -55,7 +56,8 @@ def main():
     n_tiles = len(tiles.top_left_coordinates(args.size, args.size, args.patch))
     if args.mode == "sp":
         trainer = initialize_trainer("wesup", device=dev, pretrained=False, hc_dtype=hc_dtype,
-                                     materialize_hypercolumn=args.materialize, cuda_graph=not args.no_graph)
+                                     materialize_hypercolumn=args.materialize, cuda_graph=not args.no_graph,
+                                     footprints=not args.no_footprints)
         trainer.model.eval()
         step, prefetch = trainer.predict_labels, trainer.prefetch
         out_dtype = torch.uint8

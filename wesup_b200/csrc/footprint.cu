@@ -851,41 +851,43 @@ __global__ void __launch_bounds__(BC_THREADS, 6) fp_pool_bwd_cells_kernel(const 
     }
 }
 
-// full-resolution levels: grad[p, c] = grad_pooled[row(p), c] / |S_row(p)|; four pixels per thread so that
-// the label -> count -> row chain of four pixels is in flight together
+// full-resolution levels: grad[p, c] = grad_pooled[row(p), c] / |S_row(p)|.  A warp takes 32 consecutive pixels: label and
+// 1/|S| of pixel p0 + lane are loaded once, lane-parallel, and broadcast with shuffles; the pooled-gradient row
+// (L2-resident) is re-fetched only when the label changes along the run (a superpixel is ~14 pixels wide), so the
+// steady state is shuffle, shuffle, four multiplies, one 128-bit streaming store per pixel.
 __global__ void __launch_bounds__(256) fp_pool_bwd_ident_kernel(const Levels L, const PoolGroup bg, const float *__restrict__ gp,
                                                                 const int32_t *__restrict__ row_labels,
                                                                 const int32_t *__restrict__ counts, long HW) {
-    const int nch4 = bg.Cg >> 2, Ctot = L.Ctot;
-    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;                                      // host: items < 2^32
-    const unsigned quad = idx / (unsigned)nch4;
-    const int c4 = (int)(idx - quad * (unsigned)nch4);
-    const long p0 = (long)quad * 4;
+    const int lane = threadIdx.x & 31;
+    const long p0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
     if (p0 >= HW) return;
-    int lab[4];
-    if (p0 + 3 < HW && (reinterpret_cast<uintptr_t>(row_labels) & 15u) == 0) {
-        const int4 t = __ldg(reinterpret_cast<const int4 *>(row_labels + p0));
-        lab[0] = t.x; lab[1] = t.y; lab[2] = t.z; lab[3] = t.w;
-    } else {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) lab[u] = p0 + u < HW ? __ldg(row_labels + p0 + u) : -1;
+    const int nch4 = bg.Cg >> 2, Ctot = L.Ctot;
+    const int np = (int)min(32L, HW - p0);
+    int my_lab = -1;
+    float my_scale = 0.f;
+    if (lane < np) {
+        my_lab = __ldg(row_labels + p0 + lane);
+        const int cnt = __ldg(counts + my_lab);
+        my_scale = cnt > 0 ? 1.0f / (float)cnt : 0.f;
     }
-    int cnt[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) cnt[u] = lab[u] >= 0 ? __ldg(counts + lab[u]) : 0;
-    float4 val[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-        val[u] = lab[u] >= 0 ? __ldg(reinterpret_cast<const float4 *>(gp + bg.coff + (long)lab[u] * Ctot) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    int l, cl;
-    locate_level(L, bg.l0, bg.l1, c4 << 2, l, cl);
-    float *__restrict__ dst = L.dst[l] + cl;
-    const int Cl = L.C[l];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        if (p0 + u < HW) {
-            const float wv = cnt[u] > 0 ? 1.0f / (float)cnt[u] : 0.f;
-            stg_stream(reinterpret_cast<float4 *>(dst + (p0 + u) * Cl), wv * val[u]);
+    for (int cb = 0; cb < nch4; cb += 32) {
+        const int c4 = cb + lane;
+        const bool live = c4 < nch4;
+        int l = bg.l0, cl = 0;
+        if (live) locate_level(L, bg.l0, bg.l1, c4 << 2, l, cl);
+        const int Cl = L.C[l];
+        float *__restrict__ dst = L.dst[l] + cl + p0 * Cl;
+        const float *__restrict__ src = gp + bg.coff + (c4 << 2);
+        int prev = -1;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < np; ++i) {
+            const int lab = __shfl_sync(0xffffffffu, my_lab, i);
+            const float sc = __shfl_sync(0xffffffffu, my_scale, i);
+            if (lab != prev) {                              // warp-uniform
+                if (live) val = __ldg(reinterpret_cast<const float4 *>(src + (long)lab * Ctot));
+                prev = lab;
+            }
+            if (live) stg_stream(reinterpret_cast<float4 *>(dst + (long)i * Cl), sc * val);
         }
     }
 }
@@ -1111,19 +1113,19 @@ extern "C" int wesup_levels_pool_bwd_fp(const float *grad_pooled, const int32_t 
     AuxStream *aux = ((B.n > 0 || BC.n > 0) && any_ident) ? aux_stream() : nullptr;
     if (aux && cudaEventRecord(aux->fork, stream) == cudaSuccess && cudaStreamWaitEvent(aux->s, aux->fork, 0) == cudaSuccess)
         s_ident = aux->s;
+    // the identity launch goes first: its 1 wave of short blocks leaves room for the list kernels to start beside it
+    const long HW = (long)H * W;
+    for (int g = 0; g < G.n; ++g) {
+        if (G.g[g].res >= 0) continue;
+        fp_pool_bwd_ident_kernel<<<cdiv(cdiv(HW, 32), 8), 256, 0, s_ident>>>(L, G.g[g], grad_pooled, row_labels, counts, HW);
+        ++launched;
+    }
     if (BC.n > 0) {
         fp_pool_bwd_cells_kernel<<<(int)cblocks, BC_THREADS, 0, stream>>>(L, P, BC, grad_pooled);
         ++launched;
     }
     if (B.n > 0) {
         fp_pool_bwd_kernel<2><<<blocks, FP_THREADS, 0, stream>>>(L, P, B, grad_pooled);
-        ++launched;
-    }
-    const long HW = (long)H * W;
-    for (int g = 0; g < G.n; ++g) {
-        if (G.g[g].res >= 0) continue;
-        const long items = ((HW + 3) / 4) * (G.g[g].Cg / 4);
-        fp_pool_bwd_ident_kernel<<<cdiv(items, 256), 256, 0, s_ident>>>(L, G.g[g], grad_pooled, row_labels, counts, HW);
         ++launched;
     }
     if (s_ident != stream) {
