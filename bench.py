@@ -469,7 +469,7 @@ def run_own(args):
 
 def main():
     if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
-        os.environ["NCCL_DEBUG"] = "WARN"        # no version banner: stdout carries the one JSON line
+        os.environ.pop("NCCL_DEBUG", None)       # VERSION / WARN print a banner to stdout, which carries the one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
