@@ -139,7 +139,10 @@ int wesup_levels_pool_bwd(const float *grad_pooled, const int32_t *row_labels, c
  * kernels are then prologue-free streaming gathers; results equal wesup_levels_pool_fwd/bwd
  * up to fp32 summation order.  `h`, `w`, H, W, N must be the ones the blob was built with;
  * rows k with an empty CSR segment pool to zero (fixed-capacity callers, CUDA graphs).
- * Any C[l] % 4 == 0. */
+ * Any C[l] % 4 == 0.  Levels of 32/64/128/256/512 channels (forward) and 128/256/512 (backward)
+ * take the whole-cell kernels -- a warp reads / writes complete C[l]*4-byte cell rows; other
+ * channel counts take the 128-channel-chunk kernels, which the environment variables
+ * WESUP_FP_FWD=chunks / WESUP_FP_BWD=chunks also select (cross-check hook of the tests). */
 size_t wesup_footprint_bytes(const int *h, const int *w, int n_levels, int H, int W, int N);
 int wesup_footprint_build(const int *h, const int *w, int n_levels, int H, int W, int N,
                           const int32_t *seg_offsets, const int32_t *seg_pixels,

@@ -210,3 +210,20 @@ def test_folder_datasets_follow_the_reference_contract(tmp_path):
     assert half.shape == (3, 10, 15)
     (root / "masks" / "a.png").unlink(); (root / "masks").rmdir()
     assert is_empty_tensor(SegmentationDataset(root, train=False)[0][1])
+
+
+def test_level_sizes_follow_the_backbone_arithmetic():
+    """`WESUP._level_sizes` (what the footprint build is planned with, before the backbone runs) against the
+    shapes the VGG16 convolutions actually produce (/root/reference/models/wesup.py:205-210 hooks the same layers)."""
+    import torch
+    from torch import nn
+    from wesup_b200.models import WESUP
+    model = WESUP(pretrained=False)
+    for h, w in ((37, 51), (96, 112), (400, 400)):
+        x, seen = torch.zeros(1, 3, h, w), []
+        with torch.no_grad():
+            for layer in model.backbone:
+                x = layer(x)
+                if isinstance(layer, nn.Conv2d):
+                    seen.append((x.size(2), x.size(3)))
+        assert model._level_sizes(h, w) == seen

@@ -317,20 +317,22 @@ __global__ void __launch_bounds__(FP_THREADS) fp_build_bwd_kernel(const FpPlan P
     __shared__ int keys_all[FP_WARPS][FP_SLOTS];
     __shared__ unsigned wfix_all[FP_WARPS][FP_SLOTS];
     __shared__ Staged list_all[FP_WARPS][FP_SLOTS];
+    __shared__ int s_nl[FP_WARPS];
+    __shared__ int s_base;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int r = P.n - 1;                                    // coarse resolutions (longest footprint walks) own the first blocks
     while (r > 0 && (int)blockIdx.x >= P.r[r].blk1) --r;
     const FpRes &R = P.r[r];
     const int blk = (int)blockIdx.x - (r == P.n - 1 ? 0 : P.r[r + 1].blk1);
     const long q = (long)blk * FP_WARPS + wid;
-    if (q >= (long)R.h * R.w) return;
+    const bool active = q < (long)R.h * R.w;            // no early exit: the block allocates its lists together
     const int W = P.W;
     int *keys = keys_all[wid];
     unsigned *wfix = wfix_all[wid];
     Staged *list = list_all[wid];
-    const int i = (int)(q / R.w), j = (int)(q - (long)i * R.w);
+    const int i = active ? (int)(q / R.w) : 0, j = active ? (int)(q - (long)i * R.w) : 0;
     const int ylo = __ldg(R.ylo + i), xlo = __ldg(R.xlo + j);
-    const int nx = __ldg(R.xn + j), nf = __ldg(R.yn + i) * nx;
+    const int nx = __ldg(R.xn + j), nf = active ? __ldg(R.yn + i) * nx : 0;
     const float *__restrict__ wyt = R.wy + (long)i * R.ky;
     const float *__restrict__ wxt = R.wx + (long)j * R.kx;
     const float inv_nx = 1.0f / (float)nx;
@@ -341,19 +343,12 @@ __global__ void __launch_bounds__(FP_THREADS) fp_build_bwd_kernel(const FpPlan P
         s.lab = (s.w != 0.f) ? __ldg(row_labels + (long)(ylo + a) * W + xlo + b) : -1;
         return s;
     };
-    auto alloc = [&](int nl) {
-        int base = 0;
-        if (lane == 0) {
-            base = atomicAdd(R.cursor + 1, nl);
-            R.bwd_span[q] = make_int2(base, nl);
-        }
-        return __shfl_sync(0xffffffffu, base, 0);
-    };
     auto emit = [&](FpEnt *dst, int lab, float w) {
         const int cnt = __ldg(counts + lab);
         dst->idx = lab;
         dst->w = cnt > 0 ? w / (float)cnt : 0.f;
     };
+    // ---- phase 1: the list (fast path) or its length (slow path) -----------------------------------------
     keys[lane] = -1; keys[lane + 32] = -1;
     wfix[lane] = 0u; wfix[lane + 32] = 0u;
     __syncwarp();
@@ -383,6 +378,7 @@ __global__ void __launch_bounds__(FP_THREADS) fp_build_bwd_kernel(const FpPlan P
     }
     overflow = __any_sync(0xffffffffu, overflow);
     __syncwarp();
+    int nl = 0, first = INT_MAX;
     if (!overflow) {
         // rank the occupied slots by key -> list sorted by superpixel row
         const int k0 = keys[lane], k1 = keys[lane + 32];
@@ -399,19 +395,14 @@ __global__ void __launch_bounds__(FP_THREADS) fp_build_bwd_kernel(const FpPlan P
         const float finv = R.finv;
         if (k0 >= 0) { list[r0].lab = k0; list[r0].w = (float)wfix[lane] * finv; }
         if (k1 >= 0) { list[r1].lab = k1; list[r1].w = (float)wfix[lane + 32] * finv; }
-        __syncwarp();
-        const int nl = __popc(occ0) + __popc(occ1);
-        FpEnt *dst = R.bwd_ent + alloc(nl);
-        for (int e = lane; e < nl; e += 32) emit(dst + e, list[e].lab, list[e].w);
+        nl = __popc(occ0) + __popc(occ1);
     } else {
-        // count the distinct labels, then one pass per label in ascending order
-        int first = INT_MAX;
+        // count the distinct labels (they are then visited in ascending order, the footprint re-read for each)
         for (int t = lane; t < nf; t += 32) {
             const Staged s_ = fetch(t);
             if (s_.lab >= 0) first = min(first, s_.lab);
         }
         first = __reduce_min_sync(0xffffffffu, first);
-        int nl = 0;
         for (int cur = first; cur != INT_MAX; ++nl) {
             int nxt = INT_MAX;
             for (int t = lane; t < nf; t += 32) {
@@ -420,7 +411,26 @@ __global__ void __launch_bounds__(FP_THREADS) fp_build_bwd_kernel(const FpPlan P
             }
             cur = __reduce_min_sync(0xffffffffu, nxt);
         }
-        FpEnt *dst = R.bwd_ent + alloc(nl);
+    }
+    // ---- phase 2: ONE cursor atomic per block (all its cells belong to one resolution) ------------------------
+    if (lane == 0) s_nl[wid] = nl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w_ = 0; w_ < FP_WARPS; ++w_) tot += s_nl[w_];
+        s_base = tot > 0 ? atomicAdd(R.cursor + 1, tot) : 0;
+    }
+    __syncthreads();
+    if (!active) return;
+    int base = s_base;
+    for (int w_ = 0; w_ < wid; ++w_) base += s_nl[w_];
+    if (lane == 0) R.bwd_span[q] = make_int2(base, nl);
+    FpEnt *dst = R.bwd_ent + base;
+    // ---- phase 3: write the list ------------------------------------------------------------------------------
+    if (!overflow) {
+        for (int e = lane; e < nl; e += 32) emit(dst + e, list[e].lab, list[e].w);
+    } else {
         int e = 0;
         for (int cur = first; cur != INT_MAX; ++e) {
             float ws = 0.f;
