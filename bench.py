@@ -330,7 +330,7 @@ def run_own(args):
     lib = _lib.load()
     trainer = initialize_trainer("wesup", device=dev, pretrained=False, materialize_hypercolumn=args.materialize,
                                  pool_first=not args.no_pool_first, cuda_graph=not args.no_graph,
-                                 footprints=not args.no_footprints)
+                                 footprints=not args.no_footprints, cudnn_benchmark=args.cudnn_benchmark)
     trainer.optimizer, _ = trainer.get_default_optimizer()
     trainer.metric_funcs = [accuracy, dice]
     if world > 1:
@@ -457,7 +457,7 @@ def run_own(args):
                        "iteration": "eager" if args.no_graph else "one CUDA graph per image shape (SLIC .. SGD step), replayed",
                        "parallelism": f"dp{world}", "l2": "working set 1.8 GB/image (hypercolumn) >> 126 MB L2; "
                        "kernel microbenches flush L2 (256 MB write, then 256 MB read so no dirty lines remain) before every launch",
-                       "cudnn_tf32": bool(torch.backends.cudnn.allow_tf32)},
+                       "cudnn_tf32": bool(torch.backends.cudnn.allow_tf32), "cudnn_benchmark": bool(torch.backends.cudnn.benchmark)},
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d * ips, "d2h_bytes_per_step": 4 * ips,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
@@ -483,6 +483,7 @@ def main():
                     help="fused path over the 13 side outputs (side convs on H*W pixels) instead of pool-first")
     ap.add_argument("--no-footprints", action="store_true",
                     help="pooling kernels rebuild the superpixel footprints internally (default: built once per image on a side stream)")
+    ap.add_argument("--cudnn-benchmark", action="store_true", help="torch.backends.cudnn.benchmark = True (default: torch's default, off)")
     ap.add_argument("--no-graph", action="store_true",
                     help="eager iterations (default: one CUDA graph per image shape, captured after two eager iterations)")
     ap.add_argument("--no-prefetch", action="store_true", help="preprocess inline instead of one image ahead on a side stream")

@@ -300,6 +300,10 @@ class WESUPTrainer(BaseTrainer):
         kwargs = {**config.to_dict(), **kwargs}
         super().__init__(model, **kwargs)
         self.xentropy = partial(_cross_entropy)
+        if kwargs.get("cudnn_benchmark", False):
+            # optional: let cuDNN time its convolution algorithms per shape (the eager iterations that precede a
+            # graph capture fill its cache); same arithmetic class, the reference leaves the torch default (off)
+            torch.backends.cudnn.benchmark = True
 
     def get_default_dataset(self, root_dir, train=True, proportion=1.0):
         # PNG/CSV readers and albumentations augmentation are CPU I/O outside this
