@@ -1,5 +1,7 @@
-# SLIC change check: full parity suite + SLIC timing at 464^2 and 1516x1512
-out=gpurun_out/${1:-r02k}; mkdir -p $out
+# tile loop with reused pinned staging + cudnn.benchmark A/B
+out=gpurun_out/${1:-r02m}; mkdir -p $out
 (timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -3) | tee $out/pytest_gpu.log
-timeout 100 python tools/bench_slic.py 464 464 20 | tee $out/slic_464.json
-timeout 100 python tools/bench_slic.py 1516 1512 10 | tee $out/slic_crag.json
+timeout 300 python tools/bench_tiles.py --size 20000 --mode sp > $out/tiles_sp.json 2> $out/err.log; cat $out/tiles_sp.json
+python bench.py --steps 10 --warmup 4 --skip-kernels --skip-cpu --cudnn-benchmark > $out/bench_cudnnbench.json 2>> $out/err.log; cut -c1-330 $out/bench_cudnnbench.json
+python bench.py --steps 10 --warmup 4 --skip-kernels --skip-cpu > $out/bench_default.json 2>> $out/err.log; cut -c1-330 $out/bench_default.json
+tail -n 3 $out/err.log

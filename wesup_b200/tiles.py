@@ -115,13 +115,23 @@ def predict_tiles(step, img: np.ndarray, patch_size: int, device, rank: int = 0,
     mine = coords[lo:hi]
     use_cuda = torch.cuda.is_available() and torch.device(device).type == "cuda"
     outs = []
-    for c0 in range(0, len(mine), chunk):
+    # two pinned staging buffers, allocated once (cudaHostAlloc of a 123 MB chunk costs tens of ms) and used in
+    # turn: a buffer is rewritten only after the asynchronous copy that last read it has completed
+    n_stage = min(chunk, max(len(mine), 1))
+    stages = [torch.empty((n_stage, patch_size, patch_size, 3), dtype=torch.uint8, pin_memory=use_cuda) for _ in range(2)]
+    copied = [None, None]
+    for ci, c0 in enumerate(range(0, len(mine), chunk)):
         part = mine[c0:c0 + chunk]
-        stage = torch.empty((len(part), patch_size, patch_size, 3), dtype=torch.uint8, pin_memory=use_cuda)
+        stage = stages[ci & 1][:len(part)]
+        if copied[ci & 1] is not None:
+            copied[ci & 1].synchronize()
         stage_np = stage.numpy()
         for k, (t, l) in enumerate(part):
             stage_np[k] = img[t:t + patch_size, l:l + patch_size, :3]
         dev_u8 = stage.to(device, non_blocking=True)
+        if use_cuda:
+            copied[ci & 1] = torch.cuda.Event()
+            copied[ci & 1].record(torch.cuda.current_stream(device))
 
         def tile(k):
             return dev_u8[k].permute(2, 0, 1).float().div_(255.0).unsqueeze(0).contiguous()       # == TF.to_tensor
