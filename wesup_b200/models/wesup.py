@@ -495,9 +495,13 @@ class WESUPTrainer(BaseTrainer):
         if self.grad_sync is None:
             self.optimizer.zero_grad(set_to_none=True)
         graph = torch.cuda.CUDAGraph()
+        lib = ops._lib.load()
+        n0 = lib.wesup_kernel_launches()
         with torch.cuda.graph(graph, stream=side, **({"pool": pool} if pool is not None else {})):
             keys, out = self._static_iteration(st, step=True)
-        return {"graph": graph, "st": st, "keys": keys, "out": out, "lr": self.optimizer.param_groups[0]["lr"]}
+        # library launches recorded into the graph: every replay re-issues them without passing through the C ABI
+        return {"graph": graph, "st": st, "keys": keys, "out": out, "lr": self.optimizer.param_groups[0]["lr"],
+                "launches": int(lib.wesup_kernel_launches() - n0)}
 
     def train_one_iteration(self, phase, *data):
         use_graph = (phase == "train" and self.kwargs.get("cuda_graph", False) and len(data) in (2, 3)
@@ -539,6 +543,7 @@ class WESUPTrainer(BaseTrainer):
             return self._run_iteration(phase, input_, target)
         self._load_static(entry["st"], img, pixel_mask, sp)
         entry["graph"].replay()
+        self.replayed_launches = getattr(self, "replayed_launches", 0) + entry["launches"]
         if self.grad_sync is not None:
             self.grad_sync.average_gradients()
             self.optimizer.step()
