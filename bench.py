@@ -455,7 +455,7 @@ def run_own(args):
                         "not materialised: superpixel means from the 13 backbone levels (4224 ch), side convs on the N pooled rows"),
                        "footprints": "rebuilt inside the pooling kernels" if args.no_footprints else
                        "precomputed per image (wesup_footprint_build, forked beside the backbone)",
-                       "iteration": "eager" if args.no_graph else "one CUDA graph per image shape (SLIC .. SGD step), replayed",
+                       "iteration": "eager" if args.no_graph else "one CUDA graph per image shape (VGG16 .. SGD step) replayed; GPU SLIC + superpixel statistics run one image ahead on a side stream",
                        "parallelism": f"dp{world}", "l2": "working set 1.8 GB/image (hypercolumn) >> 126 MB L2; "
                        "kernel microbenches flush L2 (256 MB write, then 256 MB read so no dirty lines remain) before every launch",
                        "cudnn_tf32": bool(torch.backends.cudnn.allow_tf32), "cudnn_benchmark": bool(torch.backends.cudnn.benchmark)},

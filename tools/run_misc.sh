@@ -1,7 +1,4 @@
-# tile loop with reused pinned staging + cudnn.benchmark A/B
-out=gpurun_out/${1:-r02m}; mkdir -p $out
-(timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -3) | tee $out/pytest_gpu.log
-timeout 300 python tools/bench_tiles.py --size 20000 --mode sp > $out/tiles_sp.json 2> $out/err.log; cat $out/tiles_sp.json
-python bench.py --steps 10 --warmup 4 --skip-kernels --skip-cpu --cudnn-benchmark > $out/bench_cudnnbench.json 2>> $out/err.log; cut -c1-330 $out/bench_cudnnbench.json
-python bench.py --steps 10 --warmup 4 --skip-kernels --skip-cpu > $out/bench_default.json 2>> $out/err.log; cut -c1-330 $out/bench_default.json
-tail -n 3 $out/err.log
+# final check of the tree: bench.py with its defaults (own arm), smoke()
+out=gpurun_out/${1:-r02z}; mkdir -p $out
+timeout 600 python bench.py > $out/bench.json 2> $out/err.log; cut -c1-420 $out/bench.json; tail -n 3 $out/err.log
+(timeout 200 python __graft_entry__.py smoke 2>&1 | tail -1) | tee $out/smoke.log
