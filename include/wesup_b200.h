@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define WESUP_ABI_VERSION 5
+#define WESUP_ABI_VERSION 6
 #define WESUP_MAX_LEVELS 16
 
 /* element type of the hypercolumn tensor */
@@ -178,6 +178,13 @@ int wesup_sp_pool_hypercolumn_bwd_walk(const float *grad_pooled, const int32_t *
                                        const int32_t *counts, const int *C, const int *h, const int *w,
                                        int n_levels, int H, int W, int N, void *const *grad_side,
                                        void *ws, void *stream);
+
+/* ---- bias gradient of a channels_last convolution ----------------------------
+ * out[c] = sum_p x[p, c] over a pixel-major (rows, C) fp32 matrix: what autograd computes as
+ * grad_out.sum((0,2,3)) for every nn.Conv2d the reference builds (models/wesup.py:190-210).
+ * Deterministic two-stage reduction; `ws` from wesup_colsum_workspace_bytes.  C % 4 == 0, C <= 1024. */
+size_t wesup_colsum_workspace_bytes(long rows, int C);
+int wesup_colsum(const float *x, long rows, int C, float *out, void *ws, void *stream);
 
 /* ---- paint: replaces argmax + per-superpixel index_put loop -----------------
  * (models/wesup.py:295-304): out[p] = sp_pred[row_labels[p], cls]. */

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.wesup_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.wesup_abi_version() == _lib.ABI_VERSION == 6
     out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
     for name in declared:
         assert re.search(rf"\bT {name}\b", out), name

@@ -666,3 +666,40 @@ def test_slic_connectivity_matches_sequential_on_kmeans_output():
     labels, n = ops.slic(x, n_segments, 40)
     assert float((labels.cpu().numpy() == ref).mean()) >= 0.999
     assert int(n.item()) == ref_n
+
+
+# ---------------------------------------------------------------------------
+# bias gradient of the channels_last convolutions
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,c", [(1, 4), (37, 8), (215296, 64), (53824, 128), (3364, 512), (1000, 96), (841, 1024)])
+def test_colsum_vs_fp64_sum(rows, c):
+    g = torch.Generator().manual_seed(rows + c)
+    x = torch.randn(rows, c, generator=g).to(DEV)
+    out = ops.colsum(x)
+    ref = x.double().sum(0)
+    assert out.shape == (c,)
+    assert float((out.double() - ref).abs().max()) <= 1e-5 * float(x.double().abs().sum(0).max()) + 1e-6
+    assert torch.equal(out, ops.colsum(x))                          # fixed summation order
+    with pytest.raises(ValueError):
+        ops.colsum(torch.zeros(5, 6, device=DEV))                   # C % 4 != 0
+
+
+@pytest.mark.parametrize("cin,cout,k,h,w", [(3, 64, 3, 48, 40), (64, 128, 3, 37, 51), (256, 128, 1, 29, 29)])
+def test_conv2d_channels_last_matches_autograd_of_conv2d(cin, cout, k, h, w):
+    """Same forward as nn.Conv2d; input and weight gradients from the same aten op; the bias gradient (wesup_colsum)
+    equals autograd's grad.sum((0,2,3)) up to fp32 summation order."""
+    torch.manual_seed(cin + cout)
+    conv = torch.nn.Conv2d(cin, cout, k, padding=k // 2).to(DEV)
+    conv.weight.data = conv.weight.data.contiguous(memory_format=torch.channels_last)
+    x = torch.randn(1, cin, h, w, device=DEV).contiguous(memory_format=torch.channels_last)
+    g = torch.randn(1, cout, h, w, device=DEV).contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya = conv(xa)
+    ya.backward(g)
+    ref = [xa.grad.clone(), conv.weight.grad.clone(), conv.bias.grad.clone()]
+    conv.zero_grad(set_to_none=True)
+    yb = ops.conv2d_channels_last(xb, conv)
+    assert rel_err(yb, ya) < 1e-5
+    yb.backward(g)
+    assert rel_err(xb.grad, ref[0]) < 1e-4 and rel_err(conv.weight.grad, ref[1]) < 1e-4          # same aten op; cuDNN may pick another algorithm
+    assert rel_err(conv.bias.grad, ref[2]) < 1e-5

@@ -11,7 +11,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "libwesup_b200.so"
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 F32, BF16 = 0, 1
 CHW, HWC = 0, 1
@@ -43,6 +43,8 @@ SIGNATURES = {
     "wesup_levels_pool_bwd_fp": (c_int, [_vp, _vp, _vp, _ip, _ip, _ip, c_int, c_int, c_int, c_int, _vp, POINTER(_vp), _vp]),
     "wesup_hypercolumn_pool_fwd_walk": (c_int, [POINTER(_vp), _ip, _ip, _ip, c_int, c_int, c_int, _vp, _vp, c_int, _vp, _vp]),
     "wesup_sp_pool_hypercolumn_bwd_walk": (c_int, [_vp, _vp, _vp, _ip, _ip, _ip, c_int, c_int, c_int, c_int, POINTER(_vp), _vp, _vp]),
+    "wesup_colsum_workspace_bytes": (c_size_t, [ctypes.c_long, c_int]),
+    "wesup_colsum": (c_int, [_vp, ctypes.c_long, c_int, _vp, _vp, _vp]),
     "wesup_sp_paint": (c_int, [_vp, _vp, c_int, c_int, c_int, _vp, _vp]),
     "wesup_label_propagate_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "wesup_label_propagate": (c_int, [_vp, c_int, c_int, c_int, _vp, c_int, c_float, _vp, _vp, _vp, _vp, _vp]),

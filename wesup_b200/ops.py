@@ -451,6 +451,57 @@ def paint(sp: SuperpixelMaps, sp_pred: torch.Tensor, cls: int = 1) -> torch.Tens
 
 
 # ---------------------------------------------------------------------------
+# convolution whose bias gradient is a streaming column sum
+# ---------------------------------------------------------------------------
+def colsum(x2d: torch.Tensor) -> torch.Tensor:
+    """out[c] = sum_p x2d[p, c] for a contiguous (rows, C) fp32 CUDA matrix (C % 4 == 0)."""
+    lib = _lib.load()
+    _require_cuda(x2d, "x2d")
+    rows, c = x2d.shape
+    nbytes = lib.wesup_colsum_workspace_bytes(rows, c)
+    if nbytes == 0:
+        raise ValueError(f"wesup_colsum does not support a ({rows}, {c}) matrix")
+    out = torch.empty(c, dtype=torch.float32, device=x2d.device)
+    ws = _ws(nbytes, x2d.device)
+    check(lib.wesup_colsum(x2d.data_ptr(), rows, c, out.data_ptr(), ws.data_ptr(), _stream()), "wesup_colsum")
+    return out
+
+
+class _Conv2dChannelsLast(torch.autograd.Function):
+    """`F.conv2d` (cuDNN, unchanged) whose backward asks `aten::convolution_backward` for the input and weight
+    gradients only and takes the bias gradient -- autograd's `grad_out.sum((0, 2, 3))`, a generic ATen reduction
+    that reads channels_last gradients at a tenth of the HBM rate -- from `wesup_colsum`."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, dilation, groups):
+        ctx.save_for_backward(x, weight)
+        ctx.conf = (stride, padding, dilation, groups)
+        return torch.nn.functional.conv2d(x, weight, bias, stride, padding, dilation, groups)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, weight = ctx.saved_tensors
+        stride, padding, dilation, groups = ctx.conf
+        grad_out = grad_out.contiguous(memory_format=torch.channels_last)
+        gx, gw, _ = torch.ops.aten.convolution_backward(grad_out, x, weight, None, stride, padding, dilation, False, [0, 0], groups,
+                                                        [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        gb = None
+        if ctx.needs_input_grad[2]:
+            gb = colsum(grad_out.permute(0, 2, 3, 1).reshape(-1, grad_out.size(1)))
+        return gx, gw, gb, None, None, None, None
+
+
+def conv2d_channels_last(x: torch.Tensor, conv: torch.nn.Conv2d) -> torch.Tensor:
+    """`conv(x)` for a channels_last fp32 CUDA input, bias gradient through `wesup_colsum`; any other case
+    (no bias, padding modes other than zeros, channel counts the kernel does not take) is plain `conv(x)`."""
+    if (conv.bias is None or conv.padding_mode != "zeros" or not x.is_cuda or x.dtype != torch.float32
+            or conv.out_channels % 4 != 0 or conv.out_channels > 1024 or isinstance(conv.padding, str)):
+        return conv(x)
+    return _Conv2dChannelsLast.apply(x, conv.weight, conv.bias, list(conv.stride), list(conv.padding), list(conv.dilation),
+                                     conv.groups)
+
+
+# ---------------------------------------------------------------------------
 # (c) label propagation
 # ---------------------------------------------------------------------------
 _LP_ALGOS = {"auto": "wesup_label_propagate", "exact": "wesup_label_propagate_exact", "tc": "wesup_label_propagate_tc"}
