@@ -66,6 +66,18 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_tools() -> Path:
+    """tools/l2bw.cu -> tools/_l2bw: the stand-alone L2 / HBM gather microbenchmark quoted in DESIGN.md section 3
+    (a measurement tool, not part of the library)."""
+    src, out = PKG.parent / "tools" / "l2bw.cu", PKG.parent / "tools" / "_l2bw"
+    if src.exists() and _stale(out, [src]):
+        r = subprocess.run([_nvcc(), "-O3", "-gencode", "arch=compute_100a,code=sm_100a", str(src), "-o", str(out)],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
