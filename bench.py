@@ -283,6 +283,16 @@ def kernel_rooflines(dev, peak_gbs):
             out["levels_pool_fwd_side2112"]["replaces_ms"] = out["hypercolumn_fwd_f32"]["ms"] + out["sp_pool_fwd_f32"]["ms"]
             out["levels_pool_bwd_side2112"]["replaces_ms"] = out["sp_pool_bwd_f32"]["ms"] + out["hypercolumn_bwd_f32"]["ms"]
         del feats, gf
+    # bias gradients of the 13 backbone convolutions (channels_last conv gradients, 232 MB per image): wesup_colsum
+    grads = [torch.randn((H >> s_) * (W >> s_), 2 * c, generator=g).to(dev) for c, s_ in zip(VGG_C, VGG_SHIFT)]
+    ms = time_kernel(lambda: [ops.colsum(t) for t in grads], 10, flush)
+    b = sum(t.numel() * 4 for t in grads)
+    out["conv_bias_grad_colsum_x13"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6,
+                                        "note": "13 eager calls through Python (2 allocations + 2 launches each): host-bound here; inside the "
+                                                "training graph the same launches replace ATen reductions worth 0.37 ms per image"}
+    ms = time_kernel(lambda: [t.sum(0) for t in grads], 10, flush)
+    out["conv_bias_grad_aten_sum_x13"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6, "note": "what autograd runs without the wrapper"}
+    del grads
     ms = time_kernel(lambda: ops.slic(x, int(hw / 200), 40), 10, flush)
     b = hw * 360
     out["slic"] = {"ms": ms, "bytes": b, "gbs": b / ms / 1e6}
