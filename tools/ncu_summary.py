@@ -4,6 +4,8 @@ handful of numbers the roofline discussion uses: duration, DRAM bytes, achieved
 DRAM throughput, occupancy, hit rates, issue activity and the top stall reasons.
 
     python tools/ncu_summary.py gpurun_out/prof.ncu-rep [kernel-substring] > profiles/rNN_<kernel>.md
+
+One section per (kernel name, grid size): the first captured launch of every distinct launch shape.
 """
 import csv
 import io
@@ -44,10 +46,11 @@ def main(rep, needle=""):
         name = r[col["Kernel Name"]]
         if needle and needle not in name:
             continue
-        if name in seen:
+        grid = r[col["launch__grid_size"]] if "launch__grid_size" in col else ""
+        if (name, grid) in seen:                            # one section per kernel AND launch shape
             continue
-        seen.add(name)
-        print(f"## `{name[:120]}`\n")
+        seen.add((name, grid))
+        print(f"## `{name[:120]}`" + (f" — grid {grid}" if grid else "") + "\n")
         print("| metric | value |\n|---|---|")
         for key, label in KEYS:
             if key in col and r[col[key]] not in ("", "n/a"):
