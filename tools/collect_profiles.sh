@@ -32,6 +32,6 @@ python tools/ncu_traffic.py $out/prof_lp.ncu-rep $out/roofline_traffic_lp.json >
 ls -la $out
 for f in $out/*.ncu-rep; do
     sz=$(stat -c %s "$f")
-    if [ "$sz" -gt 15000000 ]; then echo "dropping $f ($sz bytes)"; rm -f "$f"; fi
+    if [ "$sz" -gt 24000000 ]; then echo "dropping $f ($sz bytes)"; rm -f "$f"; fi
 done
 du -sh gpurun_out
