@@ -350,11 +350,13 @@ def sp_pool(feat: torch.Tensor, sp: SuperpixelMaps, layout: str = "hwc") -> torc
 
 
 class _HypercolumnPool(torch.autograd.Function):
-    """(a) then (b) as one differentiable op over the side outputs.  Forward is the
-    two north-star kernels (the hypercolumn is written once, then pooled);
-    backward is ONE fused kernel that evaluates the adjoint of both from the
-    pooled gradient, so the (H*W, C) gradient is never materialised and nothing
-    of that size is kept for backward (both ops are linear)."""
+    """(a) then (b) as one differentiable op over the side outputs (or the backbone levels).
+    Forward: the two north-star kernels (the hypercolumn is written once, then pooled) when a
+    `dtype` is given, else the fused operator that pools straight from the levels -- over
+    precomputed `Footprints` when given, with the lists rebuilt in-kernel otherwise.
+    Backward: always the fused adjoint of both from the pooled gradient (over the same
+    footprints when they carry the backward lists), so the (H*W, C) gradient is never
+    materialised and nothing of that size is kept for backward (both ops are linear)."""
 
     @staticmethod
     def forward(ctx, sp: SuperpixelMaps, size, dtype, fp, *sides):
