@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define WESUP_ABI_VERSION 6
+#define WESUP_ABI_VERSION 7
 #define WESUP_MAX_LEVELS 16
 
 /* element type of the hypercolumn tensor */
@@ -231,11 +231,30 @@ int wesup_label_propagate_dev(const float *feats, int n_max, int D, const int32_
 /* ---- (d) SLIC: replaces skimage.segmentation.slic at models/wesup.py:471-476
  * rgb: fp32 in [0,1], (3,H,W) for WESUP_CHW (what the trainer holds) or (H,W,3).
  * labels: (H*W) int32, 0-based, contiguous, numbered in raster order of first
- * pixel; n_labels: device scalar. */
+ * pixel; n_labels: device scalar.  Connectivity enforcement applies skimage's
+ * min_size = int(0.5*H*W/n_segments) merge and max_size = int(3*H*W/n_segments) cut.
+ * Two persistent cooperative launches per call (k-means sweeps; connectivity).
+ * The _batch form runs B same-sized images (rgb (B,3,H,W) or (B,H,W,3), labels
+ * (B,H*W), n_labels (B)) in the same two launches; results equal B single calls
+ * bit for bit (integer / fixed-point cluster sums). */
 size_t wesup_slic_workspace_bytes(int H, int W, int n_segments);
 int wesup_slic(const float *rgb, int rgb_layout, int H, int W, int n_segments, double compactness,
                int max_iter, int enforce_connectivity, int32_t *labels, int32_t *n_labels,
                void *ws, void *stream);
+size_t wesup_slic_batch_workspace_bytes(int B, int H, int W, int n_segments);
+int wesup_slic_batch(const float *rgb, int rgb_layout, int B, int H, int W, int n_segments,
+                     double compactness, int max_iter, int enforce_connectivity, int32_t *labels,
+                     int32_t *n_labels, void *ws, void *stream);
+/* Measurement tooling: %globaltimer stamps (ns) that block 0 wrote after every grid barrier of the last
+ * wesup_slic[_batch] call on `ws`; out_host[64].  Synchronises the device. */
+int wesup_slic_debug_times(const void *ws, int B, int H, int W, int n_segments, unsigned long long *out_host);
+/* The connectivity pass alone on arbitrary int32 label maps seg (B,H*W)
+ * (skimage's _enforce_label_connectivity_cython: 4-connected pieces in raster
+ * order, breadth-first search capped at max_size, pieces below min_size merged
+ * into the last labelled neighbour seen).  Requires min_size <= max_size. */
+size_t wesup_enforce_connectivity_workspace_bytes(int B, int H, int W);
+int wesup_enforce_connectivity(const int32_t *seg, int B, int H, int W, int min_size, int max_size,
+                               int32_t *labels, int32_t *n_labels, void *ws, void *stream);
 
 #ifdef __cplusplus
 }

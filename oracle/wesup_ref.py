@@ -108,7 +108,7 @@ def paint_dense(sp_maps: torch.Tensor, sp_pred: torch.Tensor) -> torch.Tensor:
     """Per-pixel prediction of the superpixel that owns the pixel; returns the
     class-1 plane with a leading batch dim, (1,H,W)."""
     owner = sp_maps.argmax(dim=0)                           # :295
-    canvas = torch.zeros(*owner.shape, sp_pred.size(1))
+    canvas = torch.zeros(*owner.shape, sp_pred.size(1), device=sp_pred.device)
     for k in range(int(owner.max()) + 1):                   # :301-302
         canvas[owner == k] = sp_pred[k]
     return canvas.unsqueeze(0)[..., 1]
@@ -133,6 +133,97 @@ def label_propagate(features: torch.Tensor, y_l: torch.Tensor, threshold: float 
     if return_aux:
         return y_u, src, best
     return y_u
+
+
+# ---------------------------------------------------------------------------
+# Scalable forms of the same definitions, for the BASELINE shapes where the dense
+# formulation cannot be held (CRAG 1516x1512: dense sp_maps = 105 GB, hypercolumn
+# = 19 GB, (N,N,D) affinity = 17 GB).  Each is checked against its dense twin above
+# at small sizes by tests/test_oracle_golden.py before the GPU tests rely on it.
+# ---------------------------------------------------------------------------
+def superpixel_order_and_labels_counts(segments: torch.Tensor, mask: torch.Tensor | None):
+    """`superpixel_order_and_labels` from per-superpixel integer class counts (SURVEY.md Appendix
+    A.2: all classes of a superpixel share one denominator, so `dist > 0` and `dist == rowmax`
+    are decided by the counts).  Returns (order, sp_labels, counts-per-row)."""
+    seg = segments.reshape(-1).long()
+    n_sp = int(seg.max()) + 1
+    sizes = torch.bincount(seg, minlength=n_sp)
+    if mask is None or mask.dim() == 0:
+        order = torch.unique(seg)
+        return order, None, sizes[order]
+    m = mask.reshape(mask.size(0), -1).long()
+    per_class = torch.stack([torch.bincount(seg, weights=m[c].double(), minlength=n_sp).long()
+                             for c in range(m.size(0))], dim=1)              # (n_sp, C)
+    total = per_class.sum(dim=1)
+    labeled = torch.nonzero(total > 0).flatten()
+    unlabeled = torch.nonzero(total == 0).flatten()
+    order = torch.cat([labeled, unlabeled])
+    picked = per_class[labeled]
+    sp_labels = (picked == picked.max(dim=1, keepdim=True)[0]).float()
+    return order, sp_labels, sizes[order]
+
+
+def bilinear_taps(dst: torch.Tensor, in_size: int, out_size: int):
+    """(i0, i1, w0, w1) of F.interpolate(mode='bilinear', align_corners=True) along one axis, in
+    the arithmetic ATen uses for fp32 tensors: scale and source coordinate in fp32
+    (models/wesup.py:254-255)."""
+    scale = torch.tensor((in_size - 1) / (out_size - 1) if out_size > 1 else 0.0, dtype=torch.float32)
+    src = scale * dst.to(torch.float32)
+    i0 = src.floor().long().clamp_(max=in_size - 1)
+    i1 = i0 + (i0 < in_size - 1).long()
+    w1 = src - i0.to(torch.float32)
+    return i0, i1, (1.0 - w1), w1
+
+
+def hypercolumn_at_pixels(levels, size, pixels: torch.Tensor) -> torch.Tensor:
+    """Rows of the (H*W, C_total) hypercolumn for the given flat pixel ids only, fp64 accumulation
+    of fp32 tap weights; `levels` are (1,C_l,h_l,w_l) tensors (any device)."""
+    H, W = size
+    y, x = pixels // W, pixels % W
+    cols = []
+    for lv in levels:
+        _, c, h, w = lv.shape
+        y0, y1, wy0, wy1 = bilinear_taps(y.cpu(), h, H)
+        x0, x1, wx0, wx1 = bilinear_taps(x.cpu(), w, W)
+        dev = lv.device
+        y0, y1, x0, x1 = (t.to(dev) for t in (y0, y1, x0, x1))
+        wy0, wy1, wx0, wx1 = (t.to(dev).double().unsqueeze(1) for t in (wy0, wy1, wx0, wx1))
+        f = lv[0].permute(1, 2, 0)                                     # (h, w, C) view
+        top = wx0 * f[y0, x0].double() + wx1 * f[y0, x1].double()
+        bot = wx0 * f[y1, x0].double() + wx1 * f[y1, x1].double()
+        cols.append(wy0 * top + wy1 * bot)
+    return torch.cat(cols, dim=1)
+
+
+def pooled_rows_sparse(levels, size, row_of_pixel: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    """Superpixel means (models/wesup.py:284-285) of the hypercolumn for the selected rows only:
+    (len(rows), C_total) fp64.  `row_of_pixel` is the flat (H*W) row index of every pixel."""
+    out = []
+    for r in rows.tolist():
+        px = torch.nonzero(row_of_pixel == r).flatten()
+        out.append(hypercolumn_at_pixels(levels, size, px).mean(dim=0))
+    return torch.stack(out)
+
+
+def label_propagate_block(features: torch.Tensor, y_l: torch.Tensor, threshold: float = 0.95, chunk: int = 512):
+    """`label_propagate` evaluating only the (n_u, n_l) block it uses, `chunk` unlabeled rows at a
+    time, with the same per-pair fp32 arithmetic (difference, einsum over the feature axis, exp)."""
+    f = features.detach()
+    n_l = y_l.size(0)
+    lab = f[:n_l]
+    best_all, src_all = [], []
+    for lo in range(n_l, f.size(0), chunk):
+        diff = lab.unsqueeze(0) - f[lo:lo + chunk].unsqueeze(1)        # (chunk, n_l, D): f_j - f_i as at :122
+        aff = torch.exp(-torch.einsum("ijk,ijk->ij", diff, diff))
+        best, src = aff.max(dim=1)
+        best_all.append(best)
+        src_all.append(src)
+    best = torch.cat(best_all) if best_all else torch.zeros(0)
+    src = torch.cat(src_all) if src_all else torch.zeros(0, dtype=torch.long)
+    y_u = torch.zeros(best.numel(), y_l.size(1))
+    take = best > threshold
+    y_u[take] = y_l.detach()[src[take]]
+    return y_u, src, best
 
 
 # ---------------------------------------------------------------------------

@@ -103,3 +103,63 @@ def test_pixel_inference(golden):
     with torch.no_grad():
         out = model.forward_pixels(synth.to_tensor(g["img_u8"]).unsqueeze(0))
     np.testing.assert_allclose(out.numpy(), g["pred"], rtol=1e-4, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------
+# the scalable forms used by the GlaS / CRAG GPU tests must equal their dense twins
+# ---------------------------------------------------------------------------
+def test_count_form_of_preprocessing_equals_the_dense_form(golden):
+    g = golden("preprocess_cases.npz")
+    cases = [(g[f"seg{i}"], g[f"mask{i}"]) for i in range(3)]
+    k = golden("kat_preprocess_4x4.npz")
+    cases.append((k["segments"], k["mask"]))
+    rng = np.random.default_rng(3)
+    seg = synth.perturbed_grid_segments(61, 47, 9, seed=4)
+    mask = np.zeros((3, 61, 47), np.int64)
+    pick = rng.random((61, 47)) < 0.1
+    cls = rng.integers(0, 3, (61, 47))
+    for c in range(3):
+        mask[c][pick & (cls == c)] = 1
+    cases.append((seg, mask))
+    for seg, mask in cases:
+        seg_t, mask_t = torch.from_numpy(seg), torch.from_numpy(mask)
+        maps, labels, order = O.preprocess_superpixels(seg_t, mask_t)
+        order_c, labels_c, counts_c = O.superpixel_order_and_labels_counts(seg_t, mask_t)
+        assert order_c.tolist() == order.tolist()
+        assert torch.equal(labels_c, labels)
+        assert counts_c.tolist() == (maps > 0).sum(dim=(1, 2)).tolist()
+        order_n, labels_n, _ = O.superpixel_order_and_labels_counts(seg_t, None)
+        assert order_n.tolist() == O.superpixel_order_and_labels(seg_t, None)[0].tolist() and labels_n is None
+
+
+def test_sparse_hypercolumn_and_pooling_equal_interpolate_and_dense_mm():
+    g = torch.Generator().manual_seed(2)
+    for h, w in ((48, 40), (37, 51), (75, 94)):                       # 75 -> 37 -> 18 -> 9 -> 4: floor-division levels
+        levels = [torch.randn(1, c, h >> s, w >> s, generator=g) for c, s in zip((8, 8, 12, 16, 16), (0, 1, 2, 3, 4))]
+        dense = O.hypercolumn_from_sides(levels, (h, w))               # (C,H,W)
+        px = torch.randperm(h * w, generator=g)[:200]
+        sparse = O.hypercolumn_at_pixels(levels, (h, w), px)
+        ref = dense.reshape(dense.size(0), -1).t()[px].double()
+        assert float((sparse - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+        seg = torch.from_numpy(synth.perturbed_grid_segments(h, w, 8, seed=h))
+        order = torch.unique(seg)
+        pooled = O.pool_dense(O.dense_sp_maps(seg, order), dense)
+        rows = torch.arange(0, order.numel(), 3)
+        sparse_pooled = O.pooled_rows_sparse(levels, (h, w), seg.reshape(-1), rows)
+        assert float((sparse_pooled - pooled[rows].double()).abs().max()) < 1e-5 * float(pooled.abs().max())
+
+
+def test_block_form_of_label_propagation_equals_the_dense_form(golden):
+    gl = golden("label_propagate_cases.npz")
+    cases = [(torch.from_numpy(gl[f"f{i}"]), torch.from_numpy(gl[f"yl{i}"])) for i in range(4)]
+    g = torch.Generator().manual_seed(1)
+    f = (torch.randn(700, 32, generator=g) * 0.06).abs()
+    yl = torch.zeros(90, 2)
+    yl[torch.arange(90), torch.randint(0, 2, (90,), generator=g)] = 1
+    cases.append((f, yl))
+    for f, yl in cases:
+        for thr in (0.8, 0.95):
+            y_u, src, best = O.label_propagate(f, yl, thr, return_aux=True)
+            y_b, src_b, best_b = O.label_propagate_block(f, yl, thr, chunk=97)
+            assert torch.equal(y_u, y_b) and torch.equal(src, src_b)
+            assert torch.allclose(best, best_b, rtol=1e-6, atol=0)

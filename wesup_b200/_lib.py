@@ -11,7 +11,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "libwesup_b200.so"
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 F32, BF16 = 0, 1
 CHW, HWC = 0, 1
@@ -55,6 +55,11 @@ SIGNATURES = {
     "wesup_label_propagate_dev": (c_int, [_vp, c_int, c_int, _vp, _vp, c_int, c_float, _vp, _vp]),
     "wesup_slic_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "wesup_slic": (c_int, [_vp, c_int, c_int, c_int, c_int, c_double, c_int, c_int, _vp, _vp, _vp, _vp]),
+    "wesup_slic_batch_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "wesup_slic_batch": (c_int, [_vp, c_int, c_int, c_int, c_int, c_int, c_double, c_int, c_int, _vp, _vp, _vp, _vp]),
+    "wesup_slic_debug_times": (c_int, [_vp, c_int, c_int, c_int, c_int, POINTER(ctypes.c_ulonglong)]),
+    "wesup_enforce_connectivity_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "wesup_enforce_connectivity": (c_int, [_vp, c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

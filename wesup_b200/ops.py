@@ -19,8 +19,18 @@ _DTYPES = {torch.float32: F32, torch.bfloat16: BF16}
 _LAYOUTS = {"chw": CHW, "hwc": HWC}
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(t: torch.Tensor) -> int:
+    """The current stream of the device `t` lives on (not of the current device)."""
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _call(name: str, t: torch.Tensor, *args) -> None:
+    """One C-ABI call on the device that owns `t`: that device is made current for the call (the
+    library launches on the current device and queries its occupancy) and the call goes onto
+    that device's current stream -- a tensor on cuda:1 never meets cuda:0's stream."""
+    lib = _lib.load()
+    with torch.cuda.device(t.device):
+        check(getattr(lib, name)(*args, _stream(t)), name)
 
 
 def _require_cuda(t: torch.Tensor, name: str) -> None:
@@ -139,10 +149,10 @@ class SuperpixelMaps:
         sp_labels = torch.empty(n_sp, n_cls, dtype=torch.float32, device=dev) if n_cls else None
         lib = _lib.load()
         ws = _ws(lib.wesup_sp_stats_workspace_bytes(h, w, n_sp, n_cls), dev)
-        check(lib.wesup_sp_stats(lab32.data_ptr(), mask64.data_ptr() if mask64 is not None else None, h, w, n_cls, n_sp,
+        _call("wesup_sp_stats", lab32, lab32.data_ptr(), mask64.data_ptr() if mask64 is not None else None, h, w, n_cls, n_sp,
                                  order.data_ptr(), row_labels.data_ptr(), counts.data_ptr(), seg_offsets.data_ptr(),
                                  seg_pixels.data_ptr(), sp_labels.data_ptr() if sp_labels is not None else None,
-                                 n_labeled.data_ptr(), ws.data_ptr(), _stream()), "wesup_sp_stats")
+                                 n_labeled.data_ptr(), ws.data_ptr())
         sp = SuperpixelMaps(h, w, n_sp, order, row_labels, counts, seg_offsets, seg_pixels, sp_labels,
                             n_labeled if n_cls else None)
         if n_sp_dev is None:
@@ -234,9 +244,9 @@ def build_footprints(sp: SuperpixelMaps, level_sizes: Sequence[Tuple[int, int]],
     fp = Footprints(_ws(nbytes, dev), hs, ws, sp.height, sp.width, sp.n, with_bwd)
 
     def launch():
-        check(lib.wesup_footprint_build(ha, wa, len(hs), sp.height, sp.width, sp.n, sp.seg_offsets.data_ptr(),
+        _call("wesup_footprint_build", sp.row_labels, ha, wa, len(hs), sp.height, sp.width, sp.n, sp.seg_offsets.data_ptr(),
                                         sp.seg_pixels.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
-                                        int(bool(with_bwd)), fp.blob.data_ptr(), _stream()), "wesup_footprint_build")
+                                        int(bool(with_bwd)), fp.blob.data_ptr())
 
     if stream is None:
         launch()
@@ -274,9 +284,8 @@ class _Hypercolumn(torch.autograd.Function):
         ctot = sum(C)
         dev = sides[0].device
         out = torch.empty((H * W, ctot) if layout == HWC else (ctot, H, W), dtype=dtype, device=dev)
-        check(lib.wesup_hypercolumn_fwd(_lib.ptr_array([m.data_ptr() for m in mem]), _lib.int_array(C), _lib.int_array(h),
-                                        _lib.int_array(w), len(sides), H, W, out.data_ptr(), _DTYPES[dtype], layout,
-                                        _stream()), "wesup_hypercolumn_fwd")
+        _call("wesup_hypercolumn_fwd", out, _lib.ptr_array([m.data_ptr() for m in mem]), _lib.int_array(C), _lib.int_array(h),
+                                        _lib.int_array(w), len(sides), H, W, out.data_ptr(), _DTYPES[dtype], layout)
         ctx.geom = (C, h, w, H, W, layout)
         return out
 
@@ -292,9 +301,9 @@ class _Hypercolumn(torch.autograd.Function):
             mem = [torch.empty((1, cc, hh, ww), dtype=torch.float32, device=dev) for cc, hh, ww in zip(C, h, w)]
         ca, ha, wa = _lib.int_array(C), _lib.int_array(h), _lib.int_array(w)
         ws = _ws(lib.wesup_hypercolumn_bwd_workspace_bytes(ca, ha, wa, len(C), H, W), dev) if layout == HWC else None
-        check(lib.wesup_hypercolumn_bwd(grad_out.data_ptr(), _DTYPES[grad_out.dtype], layout, ca, ha, wa, len(C), H, W,
+        _call("wesup_hypercolumn_bwd", grad_out, grad_out.data_ptr(), _DTYPES[grad_out.dtype], layout, ca, ha, wa, len(C), H, W,
                                         _lib.ptr_array([m.data_ptr() for m in mem]),
-                                        ws.data_ptr() if ws is not None else None, _stream()), "wesup_hypercolumn_bwd")
+                                        ws.data_ptr() if ws is not None else None)
         grads = [m.permute(0, 3, 1, 2) if layout == HWC else m for m in mem]
         return (None, None, None, *grads)
 
@@ -325,8 +334,8 @@ class _SpPool(torch.autograd.Function):
                 raise ValueError(f"features must be (C, H, W) for the chw layout, got {tuple(feat.shape)}")
             c = feat.size(0)
         pooled = torch.empty((sp.n, c), dtype=torch.float32, device=feat.device)
-        check(lib.wesup_sp_pool_fwd(feat.data_ptr(), _DTYPES[feat.dtype], layout, sp.seg_offsets.data_ptr(),
-                                    sp.seg_pixels.data_ptr(), hw, c, sp.n, pooled.data_ptr(), _stream()), "wesup_sp_pool_fwd")
+        _call("wesup_sp_pool_fwd", pooled, feat.data_ptr(), _DTYPES[feat.dtype], layout, sp.seg_offsets.data_ptr(),
+                                    sp.seg_pixels.data_ptr(), hw, c, sp.n, pooled.data_ptr())
         ctx.sp, ctx.layout, ctx.meta = sp, layout, (feat.shape, feat.dtype, c)
         return pooled
 
@@ -337,9 +346,8 @@ class _SpPool(torch.autograd.Function):
         shape, dtype, c = ctx.meta
         grad_pooled = grad_pooled.contiguous().float()
         grad_feat = torch.empty(shape, dtype=dtype, device=grad_pooled.device)
-        check(lib.wesup_sp_pool_bwd(grad_pooled.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
-                                    sp.height * sp.width, c, sp.n, grad_feat.data_ptr(), _DTYPES[dtype], ctx.layout,
-                                    _stream()), "wesup_sp_pool_bwd")
+        _call("wesup_sp_pool_bwd", grad_pooled, grad_pooled.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
+                                    sp.height * sp.width, c, sp.n, grad_feat.data_ptr(), _DTYPES[dtype], ctx.layout)
         return grad_feat, None, None
 
 
@@ -382,23 +390,19 @@ class _HypercolumnPool(torch.autograd.Function):
         if dtype is None and fp is not None:
             # fully fused over precomputed footprints: a prologue-free streaming gather
             fp.join()
-            check(lib.wesup_levels_pool_fwd_fp(ptrs, ca, ha, wa, len(sides), H, W, sp.seg_offsets.data_ptr(),
-                                               sp.seg_pixels.data_ptr(), sp.n, fp.blob.data_ptr(), pooled.data_ptr(),
-                                               _stream()), "wesup_levels_pool_fwd_fp")
+            _call("wesup_levels_pool_fwd_fp", pooled, ptrs, ca, ha, wa, len(sides), H, W, sp.seg_offsets.data_ptr(),
+                                               sp.seg_pixels.data_ptr(), sp.n, fp.blob.data_ptr(), pooled.data_ptr())
             feats = torch.empty(0, dtype=torch.float32, device=dev)
         elif dtype is None:
             # fully fused: superpixel means straight from the side outputs, no (H*W, C) tensor
-            check(lib.wesup_hypercolumn_pool_fwd(ptrs, ca, ha, wa, len(sides), H, W, sp.seg_offsets.data_ptr(),
-                                                 sp.seg_pixels.data_ptr(), sp.n, pooled.data_ptr(), _stream()),
-                  "wesup_hypercolumn_pool_fwd")
+            _call("wesup_hypercolumn_pool_fwd", pooled, ptrs, ca, ha, wa, len(sides), H, W, sp.seg_offsets.data_ptr(),
+                                                 sp.seg_pixels.data_ptr(), sp.n, pooled.data_ptr())
             feats = torch.empty(0, dtype=torch.float32, device=dev)
         else:
             feats = torch.empty((H * W, ctot), dtype=dtype, device=dev)
-            check(lib.wesup_hypercolumn_fwd(ptrs, ca, ha, wa, len(sides), H, W, feats.data_ptr(), _DTYPES[dtype], HWC,
-                                            _stream()), "wesup_hypercolumn_fwd")
-            check(lib.wesup_sp_pool_fwd(feats.data_ptr(), _DTYPES[dtype], HWC, sp.seg_offsets.data_ptr(),
-                                        sp.seg_pixels.data_ptr(), H * W, ctot, sp.n, pooled.data_ptr(), _stream()),
-                  "wesup_sp_pool_fwd")
+            _call("wesup_hypercolumn_fwd", feats, ptrs, ca, ha, wa, len(sides), H, W, feats.data_ptr(), _DTYPES[dtype], HWC)
+            _call("wesup_sp_pool_fwd", pooled, feats.data_ptr(), _DTYPES[dtype], HWC, sp.seg_offsets.data_ptr(),
+                                        sp.seg_pixels.data_ptr(), H * W, ctot, sp.n, pooled.data_ptr())
         ctx.mark_non_differentiable(feats)
         return pooled, feats
 
@@ -414,16 +418,14 @@ class _HypercolumnPool(torch.autograd.Function):
         fp = ctx.fp
         if fp is not None and fp.with_bwd:
             fp.join()
-            check(lib.wesup_levels_pool_bwd_fp(grad_pooled.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
+            _call("wesup_levels_pool_bwd_fp", grad_pooled, grad_pooled.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
                                                ca, ha, wa, len(C), H, W, sp.n, fp.blob.data_ptr(),
-                                               _lib.ptr_array([m.data_ptr() for m in mem]), _stream()),
-                  "wesup_levels_pool_bwd_fp")
+                                               _lib.ptr_array([m.data_ptr() for m in mem]))
         else:
             ws = _ws(lib.wesup_sp_pool_hypercolumn_bwd_workspace_bytes(ca, ha, wa, len(C), H, W, sp.n), dev)
-            check(lib.wesup_sp_pool_hypercolumn_bwd(grad_pooled.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
+            _call("wesup_sp_pool_hypercolumn_bwd", grad_pooled, grad_pooled.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(),
                                                     ca, ha, wa, len(C), H, W, sp.n,
-                                                    _lib.ptr_array([m.data_ptr() for m in mem]), ws.data_ptr(), _stream()),
-                  "wesup_sp_pool_hypercolumn_bwd")
+                                                    _lib.ptr_array([m.data_ptr() for m in mem]), ws.data_ptr())
         return (None, None, None, None, *[m.permute(0, 3, 1, 2) for m in mem])
 
 
@@ -447,8 +449,8 @@ def paint(sp: SuperpixelMaps, sp_pred: torch.Tensor, cls: int = 1) -> torch.Tens
     sp_pred = sp_pred.detach().contiguous().float()
     _require_cuda(sp_pred, "sp_pred")
     out = torch.empty((1, sp.height, sp.width), dtype=torch.float32, device=sp_pred.device)
-    check(lib.wesup_sp_paint(sp.row_labels.data_ptr(), sp_pred.data_ptr(), sp.height * sp.width, sp_pred.size(1), cls,
-                             out.data_ptr(), _stream()), "wesup_sp_paint")
+    _call("wesup_sp_paint", out, sp.row_labels.data_ptr(), sp_pred.data_ptr(), sp.height * sp.width, sp_pred.size(1), cls,
+                             out.data_ptr())
     return out
 
 
@@ -465,7 +467,7 @@ def colsum(x2d: torch.Tensor) -> torch.Tensor:
         raise ValueError(f"wesup_colsum does not support a ({rows}, {c}) matrix")
     out = torch.empty(c, dtype=torch.float32, device=x2d.device)
     ws = _ws(nbytes, x2d.device)
-    check(lib.wesup_colsum(x2d.data_ptr(), rows, c, out.data_ptr(), ws.data_ptr(), _stream()), "wesup_colsum")
+    _call("wesup_colsum", x2d, x2d.data_ptr(), rows, c, out.data_ptr(), ws.data_ptr())
     return out
 
 
@@ -531,12 +533,12 @@ def label_propagate(features: torch.Tensor, y_l: torch.Tensor, threshold: float 
     if n_u > 0 and n_l > 0:
         ws = _ws(lib.wesup_label_propagate_workspace_bytes(n, d, n_l), dev)
         name = _LP_ALGOS[algo]
-        check(getattr(lib, name)(features.data_ptr(), n, d, n_l, y_l.data_ptr(), n_cls, float(threshold),
-                                 y_u.data_ptr(), src.data_ptr(), sim.data_ptr(), ws.data_ptr(), _stream()), name)
+        _call(name, features, features.data_ptr(), n, d, n_l, y_l.data_ptr(), n_cls, float(threshold),
+              y_u.data_ptr(), src.data_ptr(), sim.data_ptr(), ws.data_ptr())
         if return_stats and algo == "tc":
             import ctypes
             import struct
-            torch.cuda.current_stream().synchronize()
+            torch.cuda.current_stream(dev).synchronize()
             out = (ctypes.c_ulonglong * 2)()
             check(lib.wesup_label_propagate_tc_stats(ws.data_ptr(), n, n_l, out), "wesup_label_propagate_tc_stats")
             stats = {"exact_evals": int(out[0]), "pairs": n_u * n_l,
@@ -561,9 +563,8 @@ def label_propagate_static(features: torch.Tensor, y_l_full: torch.Tensor, count
     if y_l_full.size(0) != n_max or counts_dev.dtype != torch.int32 or counts_dev.numel() < 2:
         raise ValueError("y_l_full must have n_max rows and counts_dev must be int32 {n_rows, n_labeled}")
     y_full = torch.empty((n_max, y_l_full.size(1)), dtype=torch.float32, device=features.device)
-    check(lib.wesup_label_propagate_dev(features.data_ptr(), n_max, d, counts_dev.data_ptr(), y_l_full.data_ptr(),
-                                        y_l_full.size(1), float(threshold), y_full.data_ptr(), _stream()),
-          "wesup_label_propagate_dev")
+    _call("wesup_label_propagate_dev", features, features.data_ptr(), n_max, d, counts_dev.data_ptr(), y_l_full.data_ptr(),
+                                        y_l_full.size(1), float(threshold), y_full.data_ptr())
     return y_full
 
 
@@ -592,7 +593,47 @@ def slic(img: torch.Tensor, n_segments: int, compactness: float = 10.0, max_iter
     ws = _ws(nbytes, dev)
     labels = torch.empty((h, w), dtype=torch.int32, device=dev)
     n_labels = torch.zeros(1, dtype=torch.int32, device=dev)
-    check(lib.wesup_slic(img.data_ptr(), CHW, h, w, int(n_segments), float(compactness), int(max_iter),
-                         int(bool(enforce_connectivity)), labels.data_ptr(), n_labels.data_ptr(), ws.data_ptr(), _stream()),
-          "wesup_slic")
+    _call("wesup_slic", img, img.data_ptr(), CHW, h, w, int(n_segments), float(compactness), int(max_iter),
+                         int(bool(enforce_connectivity)), labels.data_ptr(), n_labels.data_ptr(), ws.data_ptr())
     return labels, n_labels
+
+
+def slic_batch(imgs: torch.Tensor, n_segments: int, compactness: float = 10.0, max_iter: int = 10,
+               enforce_connectivity: bool = True):
+    """`slic` for B same-sized images `(B,3,H,W)` in the same launches (one Lab conversion, one persistent
+    k-means kernel, one persistent connectivity kernel): returns (labels int32 (B,H,W), n_labels int32 (B,)).
+    Every image's result equals the single-image call bit for bit."""
+    lib = _lib.load()
+    _require_cuda(imgs, "imgs")
+    if imgs.dim() != 4 or imgs.size(1) != 3:
+        raise ValueError("imgs must be (B,3,H,W)")
+    imgs = imgs.contiguous().float()
+    b, _, h, w = imgs.shape
+    nbytes = lib.wesup_slic_batch_workspace_bytes(b, h, w, int(n_segments))
+    if nbytes == 0:
+        raise ValueError(f"degenerate SLIC configuration: {b} x {h}x{w} images, n_segments={n_segments}")
+    dev = imgs.device
+    ws = _ws(nbytes, dev)
+    labels = torch.empty((b, h, w), dtype=torch.int32, device=dev)
+    n_labels = torch.zeros(b, dtype=torch.int32, device=dev)
+    _call("wesup_slic_batch", imgs, imgs.data_ptr(), CHW, b, h, w, int(n_segments), float(compactness), int(max_iter),
+          int(bool(enforce_connectivity)), labels.data_ptr(), n_labels.data_ptr(), ws.data_ptr())
+    return labels, n_labels
+
+
+def enforce_connectivity(seg: torch.Tensor, min_size: int, max_size: int):
+    """skimage's connectivity enforcement alone (the last stage of `slic`) on int label maps `(H,W)` or
+    `(B,H,W)`: 4-connected pieces in raster order, search capped at `max_size`, pieces below `min_size`
+    merged into the last labelled neighbour seen.  Returns (labels int32 like seg, n_labels int32 (B,))."""
+    lib = _lib.load()
+    _require_cuda(seg, "seg")
+    batched = seg.dim() == 3
+    seg3 = (seg if batched else seg.unsqueeze(0)).to(torch.int32).contiguous()
+    b, h, w = seg3.shape
+    dev = seg.device
+    ws = _ws(lib.wesup_enforce_connectivity_workspace_bytes(b, h, w), dev)
+    labels = torch.empty_like(seg3)
+    n_labels = torch.zeros(b, dtype=torch.int32, device=dev)
+    _call("wesup_enforce_connectivity", seg3, seg3.data_ptr(), b, h, w, int(min_size), int(max_size), labels.data_ptr(),
+          n_labels.data_ptr(), ws.data_ptr())
+    return (labels if batched else labels[0]), n_labels
