@@ -18,7 +18,8 @@ from PIL import Image
 
 from wesup_b200 import cli, parallel
 from wesup_b200.models import initialize_trainer
-from wesup_b200.tiles import combine_patches_to_image, divide_image_to_patches, predict_tiles  # noqa: F401  (re-exported)
+from wesup_b200.tiles import (SuperpixelTileEngine, combine_patches_to_image, divide_image_to_patches,  # noqa: F401  (re-exported)
+                              predict_tiles)
 from wesup_b200.utils.data import imread
 
 
@@ -26,9 +27,13 @@ def predict(trainer, img_path, patch_size, device="cuda", rank=0, world_size=1):
     """(H,W) prediction for one image (rank 0; None on the other ranks)."""
     img = imread(img_path) if not isinstance(img_path, np.ndarray) else img_path
 
-    # SLIC + superpixel statistics of tile k+1 run on a side stream while tile k is in the network
-    return predict_tiles(trainer.predict_labels, img, patch_size, device, rank, world_size, out_dtype=torch.uint8,
-                         prefetch=trainer.prefetch)
+    # batches of tiles: one batched GPU SLIC + VGG16 at batch size per step, preprocessing one batch ahead on a side
+    # stream, predictions merged on the device (wesup_b200.tiles)
+    engine = getattr(trainer, "_tile_engine", None)
+    if engine is None:
+        engine = trainer._tile_engine = SuperpixelTileEngine(trainer, batch=int(trainer.kwargs.get("tile_batch", 16)),
+                                                             use_graph=bool(trainer.kwargs.get("cuda_graph", True)))
+    return predict_tiles(engine, img, patch_size, device, rank, world_size)
 
 
 def save_predictions(predictions, img_paths, output_dir="predictions"):

@@ -17,15 +17,13 @@ from PIL import Image
 
 from wesup_b200 import parallel
 from wesup_b200.models.wesup import WESUPPixelInference
-from wesup_b200.tiles import GraphedStep, predict_tiles
+from wesup_b200.tiles import PixelTileEngine, predict_tiles
 from wesup_b200.utils.data import imread
 
 
-def predict(model, img, patch_size, device, rank=0, world_size=1, step=None):
-    def eager(x):
-        with torch.no_grad():
-            return model(x)[..., 1]
-    return predict_tiles(step or eager, img, patch_size, device, rank, world_size)
+def predict(model, img, patch_size, device, rank=0, world_size=1, engine=None):
+    """Class-1 probability (H,W) of `img` (rank 0; None elsewhere), tiles in batches (one CUDA graph per batch shape)."""
+    return predict_tiles(engine or PixelTileEngine(model), img, patch_size, device, rank, world_size)
 
 
 def main(argv=None):
@@ -50,12 +48,9 @@ def main(argv=None):
     model.eval()
     if rank == 0:
         print("Making inference ...")
-    def eager(x):
-        with torch.no_grad():
-            return model(x)[..., 1]
-    step = GraphedStep(eager)          # every full tile has the same shape: one CUDA graph, replayed
+    engine = PixelTileEngine(model)    # every full tile has the same shape: one CUDA graph per batch, replayed
     for img_path in sorted((data_root / "images").iterdir()):
-        final = predict(model, imread(img_path), args.patch_size, device, rank, world, step=step)
+        final = predict(model, imread(img_path), args.patch_size, device, rank, world, engine=engine)
         if rank == 0:
             Image.fromarray(np.round(final).astype("uint8") * 255).save(output_dir / img_path.name)
 

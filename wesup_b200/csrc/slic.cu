@@ -24,7 +24,7 @@
 // so the result is bit-reproducible run to run and independent of the batch size.
 #include "common.cuh"
 #include <math_constants.h>
-#include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace wesup {
 
@@ -56,9 +56,11 @@ __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &phase)
         __threadfence();
         atomicAdd(counter, 1u);
         unsigned seen;
-        do {
+        while (true) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-        } while (seen < target);
+            if (seen >= target) break;
+            __nanosleep(40);
+        }
         __threadfence();
         if (blockIdx.x == 0 && phase < 31) reinterpret_cast<unsigned long long *>(counter)[phase] = global_timer_ns();
     }
@@ -815,6 +817,12 @@ static int coresident_blocks(const void *kernel, int block_threads, int slot, in
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block_threads, 0);
     if (e != cudaSuccess) { set_error("occupancy query: %s", cudaGetErrorString(e)); return (int)e; }
+    // WESUP_SLIC_BLOCKS_PER_SM (tuning knob): fewer resident blocks per SM leave room for the kernels of other streams
+    // (the training graph runs beside the one-image-ahead preprocessing); each block then loops over more tiles
+    if (const char *env = getenv("WESUP_SLIC_BLOCKS_PER_SM")) {
+        const int lim = atoi(env);
+        if (lim > 0 && lim < per_sm) per_sm = lim;
+    }
     *out = sms * per_sm;
     if (*out <= 0) { set_error("kernel does not fit an SM"); return WESUP_E_UNSUPPORTED; }
     if (dev >= 0 && dev < 64) cache[slot][dev] = *out;

@@ -82,11 +82,14 @@ class BaseTrainer(ABC):
         pass
 
     # ---- data parallelism (additive) ---------------------------------------
-    def enable_data_parallel(self, process_group=None):
-        """Average gradients over the ranks of `process_group` every iteration."""
+    def enable_data_parallel(self, process_group=None, overlap=True, bucket_mb=10.0):
+        """Average gradients over the ranks of `process_group` every iteration: bucketed all-reduces
+        started from autograd hooks while backward is still running (`overlap=False`: after backward)."""
         from ..parallel import GradientAllReduce
-        self.grad_sync = GradientAllReduce(self.model, process_group)
+        self.grad_sync = GradientAllReduce(self.model, process_group, bucket_mb=bucket_mb)
         self.grad_sync.broadcast_parameters()
+        if overlap:
+            self.grad_sync.enable_overlap()
         return self.grad_sync
 
     # ---- checkpoints (key names are part of the surface) --------------------
@@ -140,7 +143,7 @@ class BaseTrainer(ABC):
                     metrics["loss"] = loss.detach()
                     loss.backward()
                     if self.grad_sync is not None:
-                        self.grad_sync.average_gradients()
+                        self.grad_sync.finish()          # buckets were started from the backward hooks; wait for them
                     self.optimizer.step()
             pred, target = self.postprocess(pred, target)
             metrics.update(self.evaluate(pred, target))
@@ -210,6 +213,10 @@ class BaseTrainer(ABC):
                     self.train_one_iteration(phase, *data)
                 except RuntimeError as ex:       # same policy as the reference (base.py:234-237)
                     self.logger.exception(ex)
+                    if self.grad_sync is not None and self.grad_sync.world_size > 1:
+                        # a rank that skips an iteration skips its collectives and the other ranks would block in
+                        # theirs: with data parallelism the error ends the job instead of being swallowed
+                        raise
                 data = upcoming
             self.flush_metrics()
             self.logger.info(f"Took {time.time() - start:.2f}s.")

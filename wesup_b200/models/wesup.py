@@ -297,6 +297,24 @@ class WESUPPixelInference(WESUP):
             out = self.classifier(self.fc_layers(feats))
         return out.view(height, width, -1)
 
+    def forward_batch(self, x):
+        """`forward` for a batch of same-sized tiles `(B,3,H,W)` -> `(B,H,W,C)`: VGG16 and the side convolutions run
+        once at batch size B, the hypercolumn kernel once per tile, the MLP on all B*H*W rows at once."""
+        b, _, height, width = x.shape
+        self.fm_size = (height, width)
+        sides = self._side_outputs(x)
+        hw = height * width
+        feats = torch.empty((b * hw, self.fm_channels_sum), dtype=self.hc_dtype, device=x.device)
+        for t in range(b):
+            ops.hypercolumn_into([s[t:t + 1] for s in sides], self.fm_size, feats[t * hw:(t + 1) * hw])
+        if feats.dtype == torch.bfloat16:
+            with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+                logits = self.classifier[0](self.fc_layers(feats))
+            out = torch.softmax(logits.float(), dim=1)
+        else:
+            out = self.classifier(self.fc_layers(feats))
+        return out.view(b, height, width, -1)
+
 
 class WESUPTrainer(BaseTrainer):
     """Reference: models/wesup.py:403-547."""
@@ -451,7 +469,9 @@ class WESUPTrainer(BaseTrainer):
         self.model.sp_pred = None
         metrics["loss"] = loss.detach()
         loss.backward()
-        if step and self.grad_sync is None:
+        if self.grad_sync is not None:
+            self.grad_sync.finish()               # the bucketed all-reduces started by the backward hooks (captured too)
+        if step:
             self.optimizer.step()
         self._defer_scalars = True
         try:
@@ -498,15 +518,25 @@ class WESUPTrainer(BaseTrainer):
         torch.cuda.synchronize(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):                       # warm-up of the static path: no parameter update
-            self._static_iteration(st, step=False)
+        if self.grad_sync is not None:
+            self.grad_sync.suspended = True                 # the warm-up run is local: ranks capture at different times
+        try:
+            with torch.cuda.stream(side):                   # warm-up of the static path: no parameter update, no collective
+                self._static_iteration(st, step=False)
+        finally:
+            if self.grad_sync is not None:
+                self.grad_sync.suspended = False
         torch.cuda.current_stream(dev).wait_stream(side)
         if self.grad_sync is None:
             self.optimizer.zero_grad(set_to_none=True)
         graph = torch.cuda.CUDAGraph()
         lib = ops._lib.load()
         n0 = lib.wesup_kernel_launches()
-        with torch.cuda.graph(graph, stream=side, **({"pool": pool} if pool is not None else {})):
+        # with data parallelism the NCCL watchdog thread polls events while we capture: thread-local capture mode
+        opts = {"capture_error_mode": "thread_local"} if self.grad_sync is not None else {}
+        if pool is not None:
+            opts["pool"] = pool
+        with torch.cuda.graph(graph, stream=side, **opts):
             keys, out = self._static_iteration(st, step=True)
         # library launches recorded into the graph: every replay re-issues them without passing through the C ABI
         return {"graph": graph, "st": st, "keys": keys, "out": out, "lr": self.optimizer.param_groups[0]["lr"],
@@ -553,9 +583,6 @@ class WESUPTrainer(BaseTrainer):
         self._load_static(entry["st"], img, pixel_mask, sp)
         entry["graph"].replay()
         self.replayed_launches = getattr(self, "replayed_launches", 0) + entry["launches"]
-        if self.grad_sync is not None:
-            self.grad_sync.average_gradients()
-            self.optimizer.step()
         self._submit_scalars(dict(zip(entry["keys"], entry["out"].unbind(0))), phase)
         self.flush_metrics(keep=max(int(self.kwargs.get("metrics_lag", 1) or 0), 0))
 

@@ -637,3 +637,92 @@ def enforce_connectivity(seg: torch.Tensor, min_size: int, max_size: int):
     _call("wesup_enforce_connectivity", seg3, seg3.data_ptr(), b, h, w, int(min_size), int(max_size), labels.data_ptr(),
           n_labels.data_ptr(), ws.data_ptr())
     return (labels if batched else labels[0]), n_labels
+
+
+# ---------------------------------------------------------------------------
+# forward-only helpers writing into caller-owned buffers (tiled inference: everything below runs inside one
+# CUDA graph per tile batch, so nothing here may allocate or read a host scalar)
+# ---------------------------------------------------------------------------
+class StaticSuperpixelBuffers:
+    """Fixed-capacity device buffers for the superpixel statistics of ONE image of a known size: `sp_stats_into`
+    refills them for every new label map, kernels captured in a CUDA graph keep reading the same addresses.
+    `bound` = upper bound of the superpixel count (every kept SLIC piece has >= min_size pixels); ids that do not
+    occur are empty superpixels at the end of the row order, so the first `cap >= N` rows are a complete description
+    for any cap (seg_offsets[k] == H*W for every k >= N).  With `flat` the arrays are carved out of a caller-owned
+    int32 tensor at `offset` (several images in one tensor: one copy moves them all)."""
+
+    def __init__(self, height: int, width: int, bound: int, device, flat: Optional[torch.Tensor] = None, offset: int = 0):
+        self.height, self.width, self.bound = int(height), int(width), int(bound)
+        hw = height * width
+        r4 = lambda n: (n + 3) // 4 * 4                                    # noqa: E731  (16-byte aligned sub-arrays)
+        need = 2 * r4(bound) + r4(bound + 1) + 2 * r4(hw)
+        if flat is None:
+            flat, offset = torch.empty(need, dtype=torch.int32, device=device), 0
+        if flat.dtype != torch.int32 or offset % 4 != 0 or offset + need > flat.numel():
+            raise ValueError("flat must be an int32 tensor with room for the buffers at a 16-byte aligned offset")
+        o = offset
+        self.order = flat[o:o + bound]; o += r4(bound)
+        self.counts = flat[o:o + bound]; o += r4(bound)
+        self.seg_offsets = flat[o:o + bound + 1]; o += r4(bound + 1)
+        self.row_labels = flat[o:o + hw]; o += r4(hw)
+        self.seg_pixels = flat[o:o + hw]
+        self.n_labeled = torch.zeros(1, dtype=torch.int32, device=flat.device)
+
+    def view(self, cap: int) -> SuperpixelMaps:
+        """The first `cap` rows as a `SuperpixelMaps` (no copy)."""
+        return SuperpixelMaps(self.height, self.width, cap, self.order[:cap], self.row_labels, self.counts[:cap],
+                              self.seg_offsets[:cap + 1], self.seg_pixels, None, None)
+
+
+def sp_stats_into(labels: torch.Tensor, buf: StaticSuperpixelBuffers, ws: Optional[torch.Tensor] = None) -> None:
+    """`SuperpixelMaps.from_labels(labels, None, n_sp=buf.bound)` into `buf` (labels: (H,W) int32 contiguous).
+    `ws`: workspace of wesup_sp_stats_workspace_bytes(H, W, bound, 0) bytes (allocated here when omitted)."""
+    if ws is None:
+        ws = _ws(_lib.load().wesup_sp_stats_workspace_bytes(buf.height, buf.width, buf.bound, 0), labels.device)
+    _call("wesup_sp_stats", labels, labels.data_ptr(), None, buf.height, buf.width, 0, buf.bound, buf.order.data_ptr(),
+          buf.row_labels.data_ptr(), buf.counts.data_ptr(), buf.seg_offsets.data_ptr(), buf.seg_pixels.data_ptr(), None,
+          buf.n_labeled.data_ptr(), ws.data_ptr())
+
+
+def slic_batch_into(imgs: torch.Tensor, n_segments: int, compactness: float, labels: torch.Tensor, n_labels: torch.Tensor,
+                    ws: torch.Tensor, max_iter: int = 10) -> None:
+    """`slic_batch` into caller-owned outputs and workspace (no allocation): imgs (B,3,H,W) fp32 contiguous,
+    labels (B,H,W) int32, n_labels (B,) int32, ws >= wesup_slic_batch_workspace_bytes(B,H,W,n_segments) bytes."""
+    b, _, h, w = imgs.shape
+    if not imgs.is_contiguous() or imgs.dtype != torch.float32 or labels.dtype != torch.int32 or not labels.is_contiguous():
+        raise ValueError("imgs must be contiguous fp32 (B,3,H,W) and labels contiguous int32 (B,H,W)")
+    _call("wesup_slic_batch", imgs, imgs.data_ptr(), CHW, b, h, w, int(n_segments), float(compactness), int(max_iter), 1,
+          labels.data_ptr(), n_labels.data_ptr(), ws.data_ptr())
+
+
+def levels_pool_fwd_into(levels: Sequence[torch.Tensor], size: Tuple[int, int], sp: SuperpixelMaps, out: torch.Tensor) -> None:
+    """Superpixel means straight from the feature levels (in-kernel footprints, no preprocessing) written into
+    `out (sp.n, sum C)`; `levels` are (1,C,h,w) fp32 tensors in channels_last memory (or batch slices of one)."""
+    C = [s.size(1) for s in levels]
+    h = [s.size(2) for s in levels]
+    w = [s.size(3) for s in levels]
+    mem = [_as_hwc(s) for s in levels]
+    if out.shape != (sp.n, sum(C)) or not out.is_contiguous() or out.dtype != torch.float32:
+        raise ValueError("out must be a contiguous fp32 (N, sum C) tensor")
+    _call("wesup_levels_pool_fwd", out, _lib.ptr_array([m.data_ptr() for m in mem]), _lib.int_array(C), _lib.int_array(h),
+          _lib.int_array(w), len(levels), int(size[0]), int(size[1]), sp.seg_offsets.data_ptr(), sp.seg_pixels.data_ptr(), sp.n,
+          out.data_ptr())
+
+
+def hypercolumn_into(sides: Sequence[torch.Tensor], size: Tuple[int, int], out: torch.Tensor) -> None:
+    """Kernel (a) into a caller-owned pixel-major `(H*W, sum C)` fp32 / bf16 buffer (forward only): `sides` are
+    (1,C,h,w) fp32 tensors in channels_last memory (or batch slices of one)."""
+    H, W = int(size[0]), int(size[1])
+    C = [s.size(1) for s in sides]
+    mem = [_as_hwc(s) for s in sides]
+    if out.shape != (H * W, sum(C)) or not out.is_contiguous():
+        raise ValueError("out must be a contiguous (H*W, sum C) tensor")
+    _call("wesup_hypercolumn_fwd", out, _lib.ptr_array([m.data_ptr() for m in mem]), _lib.int_array(C),
+          _lib.int_array([s.size(2) for s in sides]), _lib.int_array([s.size(3) for s in sides]), len(sides), H, W,
+          out.data_ptr(), _DTYPES[out.dtype], HWC)
+
+
+def paint_into(sp: SuperpixelMaps, sp_pred: torch.Tensor, out: torch.Tensor, cls: int = 1) -> None:
+    """`paint` into a caller-owned fp32 (H,W) buffer."""
+    _call("wesup_sp_paint", out, sp.row_labels.data_ptr(), sp_pred.data_ptr(), sp.height * sp.width, sp_pred.size(1), cls,
+          out.data_ptr())

@@ -34,16 +34,23 @@ def init_from_env(backend: str | None = None):
 
 
 class GradientAllReduce:
-    """Gradient averaging over ranks with ONE collective per step.
+    """Gradient averaging over ranks, overlapped with backward.
 
-    All parameter gradients live as views into a single flat fp32 buffer
-    (18.87 M parameters = 75.5 MB for WESUP), so `average_gradients()` is a
-    single in-place all-reduce of that buffer followed by a scale -- no
-    per-parameter launches, no copies.  Every parameter receives a gradient
-    every step on this path, so no unused-parameter
+    All parameter gradients live as views into a single flat fp32 buffer (18.87 M parameters =
+    75.5 MB for WESUP), laid out in `model.parameters()` order.  The buffer is cut into a few
+    contiguous BUCKETS; backward produces gradients in roughly reverse parameter order, so the
+    bucket at the tail of the buffer (classifier, MLP, side convolutions) is complete first and
+    the one at the head (first backbone convolutions) last.  A post-accumulate hook on every
+    parameter counts arrivals per bucket and, when a bucket is complete, starts ONE asynchronous
+    all-reduce of its slice (NCCL: ReduceOp.AVG, so no separate scaling pass) on the process
+    group's communication stream while backward keeps running on the compute stream; `finish()`
+    makes the compute stream wait for all of them before the optimizer step.  Hooks and
+    collectives are plain stream work: they are captured into the training CUDA graph, so a
+    replayed iteration needs no Python at all between backward and the SGD step.  Every parameter
+    receives a gradient every step on this path, so no unused-parameter
     handling is needed."""
 
-    def __init__(self, model: torch.nn.Module, process_group=None):
+    def __init__(self, model: torch.nn.Module, process_group=None, bucket_mb: float = 24.0):
         self.group = process_group
         self.world_size = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
@@ -52,11 +59,34 @@ class GradientAllReduce:
         total = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        self.offsets = []
         offset = 0
         for p in self.params:
-            n = p.numel()
+            self.offsets.append(offset)
             p.grad = self._view(p, offset)
-            offset += n
+            offset += p.numel()
+        backend = dist.get_backend(process_group) if dist.is_initialized() else None
+        self._avg = backend == "nccl"                      # gloo has no AVG: sum, then scale
+        # buckets: contiguous parameter ranges, filled from the tail of the buffer (first to be ready)
+        limit = int(bucket_mb * (1 << 20) / self.flat.element_size())
+        self.buckets = []                                  # (first param index, last param index + 1), tail first
+        hi = len(self.params)
+        while hi > 0:
+            lo, size = hi, 0
+            while lo > 0 and (size == 0 or size + self.params[lo - 1].numel() <= limit):
+                lo -= 1
+                size += self.params[lo].numel()
+            self.buckets.append((lo, hi))
+            hi = lo
+        self._bucket_of = {}
+        for bi, (lo, hi) in enumerate(self.buckets):
+            for i in range(lo, hi):
+                self._bucket_of[i] = bi
+        self._arrived = [0] * len(self.buckets)
+        self._works = []
+        self._hooks = []
+        self.overlap = False
+        self.suspended = False                             # True: hooks and finish() issue no collective (graph warm-up runs)
 
     def _view(self, p, offset):
         """The parameter's slot of the flat buffer, with the parameter's own strides (channels_last
@@ -66,14 +96,21 @@ class GradientAllReduce:
             return torch.as_strided(self.flat, p.size(), p.stride(), offset)
         return self.flat[offset:offset + p.numel()].view_as(p)
 
+    def bucket_slice(self, bi: int) -> torch.Tensor:
+        lo, hi = self.buckets[bi]
+        end = self.offsets[hi] if hi < len(self.params) else self.flat.numel()
+        return self.flat[self.offsets[lo]:end]
+
     def zero_grad(self):
         """Use instead of optimizer.zero_grad(set_to_none=True), which would drop the views."""
         self.flat.zero_()
+        self._arrived = [0] * len(self.buckets)
+        self._works = []
 
-    def _rebind(self):
-        offset = 0
-        for p in self.params:
-            n = p.numel()
+    def rebind(self):
+        """Re-attach any gradient that was replaced (e.g. by optimizer.zero_grad(set_to_none=True)) to its
+        slot of the flat buffer.  Not needed on the iteration path, which never drops the views."""
+        for p, offset in zip(self.params, self.offsets):
             view = self._view(p, offset)
             if p.grad is None:
                 view.zero_()
@@ -81,13 +118,58 @@ class GradientAllReduce:
             elif p.grad.data_ptr() != view.data_ptr():
                 view.copy_(p.grad)
                 p.grad = view
-            offset += n
+
+    def _reduce(self, t: torch.Tensor, async_op: bool):
+        if self._avg:
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
+        work = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+        if not async_op:
+            t.div_(self.world_size)
+        return work
+
+    # -- overlapped path ---------------------------------------------------------------------
+    def enable_overlap(self):
+        """Install the per-parameter hooks that start a bucket's all-reduce as soon as backward has
+        produced its last gradient."""
+        if self.overlap:
+            return
+        self.overlap = True
+        for i, p in enumerate(self.params):
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
+
+    def _make_hook(self, index: int):
+        bi = self._bucket_of[index]
+        lo, hi = self.buckets[bi]
+
+        def hook(_param):
+            if self.suspended:
+                return
+            self._arrived[bi] += 1
+            if self._arrived[bi] == hi - lo and self.world_size > 1:
+                self._works.append((bi, self._reduce(self.bucket_slice(bi), async_op=True)))
+        return hook
+
+    def finish(self):
+        """After backward: the compute stream waits for every bucket (any bucket whose hook did not
+        fire -- e.g. hooks disabled -- is reduced here)."""
+        if self.world_size == 1 or self.suspended:
+            return
+        started = {bi for bi, _ in self._works}
+        for bi in range(len(self.buckets)):
+            if bi not in started:
+                self._works.append((bi, self._reduce(self.bucket_slice(bi), async_op=True)))
+        for bi, work in self._works:
+            if work is not None:
+                work.wait()
+            if not self._avg:
+                self.bucket_slice(bi).div_(self.world_size)
+        self._works = []
+        self._arrived = [0] * len(self.buckets)
 
     def average_gradients(self):
-        self._rebind()
-        if self.world_size > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.div_(self.world_size)
+        """Blocking form (no overlap): one all-reduce per bucket after backward."""
+        self.rebind()
+        self.finish()
 
     def broadcast_parameters(self, src: int = 0):
         if self.world_size > 1:
