@@ -491,6 +491,16 @@ def kernel_rooflines(dev, peak_gbs, h=None, w=None, materialized=True):
 # ---------------------------------------------------------------------------
 # own arm: training step
 # ---------------------------------------------------------------------------
+def end_process(world):
+    """Leave without tearing NCCL down collectively: ranks finish at different times (rank 0 goes on to the kernel
+    microbenchmarks and the baselines) and CUDA graphs that captured NCCL kernels outlive the trainer through reference
+    cycles; a communicator destroyed under them can block interpreter shutdown.  Everything is flushed; the process ends."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        os._exit(0)
+
+
 def init_dist():
     import torch
     from wesup_b200 import parallel
@@ -538,8 +548,8 @@ def run_train(args):
                                  footprints=not args.no_footprints, cudnn_benchmark=not args.no_cudnn_benchmark)
     trainer.optimizer, _ = trainer.get_default_optimizer()
     trainer.metric_funcs = [accuracy, dice]
-    if world > 1:
-        trainer.enable_data_parallel(overlap=not args.no_overlap)
+    if (world > 1 or args.dp_at_1) and not args.no_dp:
+        trainer.enable_data_parallel(overlap=not args.no_overlap, bucket_mb=args.bucket_mb)
     ips = args.images_per_step
     pool = max(ips, 4)
     host = [synth.sample(h, w, index=rank * pool + i) for i in range(pool)]
@@ -580,9 +590,7 @@ def run_train(args):
     e2e_value = world * ips * args.steps / (ms_e2e / 1e3)
     peak_mem = torch.cuda.max_memory_allocated(dev) / 2**30
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return end_process(world)
     del trainer, resident
     torch.cuda.empty_cache()
     peak, peak_src = peaks()
@@ -637,7 +645,7 @@ def run_train(args):
                        "footprints": "rebuilt inside the pooling kernels" if args.no_footprints else
                        "precomputed per image (wesup_footprint_build, forked beside the backbone)",
                        "iteration": "eager" if args.no_graph else "one CUDA graph per image shape (VGG16 .. gradient all-reduce .. SGD step) replayed; GPU SLIC + superpixel statistics run one image ahead on a side stream",
-                       "parallelism": f"dp{world}" + ("" if world == 1 else (", blocking all-reduce" if args.no_overlap else ", bucketed all-reduce overlapped with backward, captured in the graph")),
+                       "parallelism": ("replicas (diagnosis)" if args.no_dp else f"dp{world}") + ("" if world == 1 or args.no_dp else (", blocking all-reduce" if args.no_overlap else ", bucketed all-reduce overlapped with backward, captured in the graph")),
                        "l2": "activations of one image (0.25 GB of backbone levels + cuDNN workspaces) >> 126 MB L2; "
                        "kernel microbenches flush L2 (256 MB write, then 256 MB read so no dirty lines remain) before every launch",
                        "cudnn_tf32": bool(torch.backends.cudnn.allow_tf32), "cudnn_benchmark": bool(torch.backends.cudnn.benchmark)},
@@ -646,8 +654,7 @@ def run_train(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "gpu_eager_baseline": eager, "peak_mem_gb": peak_mem, "kernels": kernels}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    end_process(world)
 
 
 # ---------------------------------------------------------------------------
@@ -725,9 +732,7 @@ def run_tiles(args):
     value = n_tiles * args.steps / (ms_total / 1e3)
     e2e_value = n_tiles * args.steps / (ms_e2e / 1e3)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return end_process(world)
     assert merged[0].shape[:2] == (args.slide, args.slide)
     out_bytes = merged[0].size * merged[0].itemsize
     line = {"metric": metric_name(args.workload, 0, 0), "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
@@ -746,8 +751,7 @@ def run_tiles(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": None, "cpu_baseline": None,
             "positive_fraction": float(np.mean(merged[0] > 0.5))}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    end_process(world)
 
 
 def _sp_engine(trainer, args):
@@ -825,6 +829,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true",
                     help="eager iterations (default: one CUDA graph per image shape, captured after two eager iterations)")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: blocking gradient all-reduce after backward instead of overlapped buckets")
+    ap.add_argument("--no-dp", action="store_true", help="N>1 diagnosis: independent replicas, no gradient exchange (NOT data-parallel training)")
+    ap.add_argument("--dp-at-1", action="store_true", help="N=1 diagnosis: gradients as views of the flat all-reduce buffer, no collective")
+    ap.add_argument("--bucket-mb", type=float, default=10.0, help="N>1: gradient bucket size")
     ap.add_argument("--no-prefetch", action="store_true", help="preprocess inline instead of one image ahead on a side stream")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-eager", action="store_true", help="omit the gpu_eager_baseline leg")

@@ -228,6 +228,17 @@ int wesup_label_propagate_tc_stats(const void *ws, int N, int n_l, unsigned long
 int wesup_label_propagate_dev(const float *feats, int n_max, int D, const int32_t *counts_dev,
                               const float *y_l, int n_cls, float thr, float *y_full, void *stream);
 
+/* ---- pixel-wise inference: first MLP layer without the hypercolumn ----------------
+ * out[p, :] = act(bias + sum_g bilinear_align_corners(z[g])[p, :]) for n_terms <= 5 pixel-major terms
+ * z[g] (h[g], w[g], C) of one dtype (WESUP_F32 / WESUP_BF16), out (H*W, C) in the same dtype, bias (C) fp32 or
+ * NULL, relu != 0 applies max(., 0).  With z[g] = cat_{levels of resolution g}(backbone level) . W'_g^T this is
+ * ReLU(Linear(2112,1024)(hypercolumn)) of WESUPPixelInference.forward (models/wesup.py:392-400, :246-261) by
+ * linearity of the 1x1 side convolutions, the upsampling and the Linear layer -- the GEMMs run at the levels' own
+ * resolution and the (H*W, 2112) tensor is never formed.  `z`, `h`, `w` are HOST arrays.  C % 4 == 0 (fp32) or
+ * C % 8 == 0 (bf16), C <= 1024 / 2048. */
+int wesup_upsample_sum(const void *const *z, const int *h, const int *w, int n_terms, int H, int W, int C,
+                       int dtype, const float *bias, int relu, void *out, void *stream);
+
 /* ---- (d) SLIC: replaces skimage.segmentation.slic at models/wesup.py:471-476
  * rgb: fp32 in [0,1], (3,H,W) for WESUP_CHW (what the trainer holds) or (H,W,3).
  * labels: (H*W) int32, 0-based, contiguous, numbered in raster order of first

@@ -106,3 +106,55 @@ def test_plain_step_functions_still_work():
     img, _ = synth.he_like_image(64, 96, seed=2)
     out = tiles.predict_tiles(lambda x: x[0, 0] * 2.0, img, 32, DEV)
     np.testing.assert_allclose(out, img[..., 0].astype(np.float32) / 255.0 * 2.0, rtol=1e-6)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("h,w", [(48, 40), (37, 51), (400, 400)])
+def test_upsample_sum_kernel_vs_interpolate(dtype, tol, h, w):
+    """out = relu(bias + sum_g bilinear(align_corners=True)(z_g)) against F.interpolate on fp32 copies of the terms."""
+    import torch.nn.functional as F
+    from wesup_b200 import ops
+    g = torch.Generator().manual_seed(h * w)
+    c = 64 if h < 400 else 1024
+    sizes = [(h, w), (h // 2, w // 2), (h // 4, w // 4), (h // 8, w // 8), (max(h // 16, 1), max(w // 16, 1))]
+    terms = [torch.randn(hh, ww, c, generator=g).to(DEV).to(dtype) for hh, ww in sizes]
+    bias = torch.randn(c, generator=g).to(DEV)
+    for n_terms in (5, 1, 3):
+        use = terms[:n_terms] if n_terms != 3 else terms[1:4]          # also: no full-resolution term
+        ref = bias.view(1, -1, 1, 1)
+        for t in use:
+            ref = ref + F.interpolate(t.float().permute(2, 0, 1).unsqueeze(0), (h, w), mode="bilinear", align_corners=True)
+        ref = torch.relu(ref)[0].permute(1, 2, 0).reshape(h * w, c)
+        out = ops.upsample_sum(use, (h, w), bias=bias, relu=True)
+        assert out.dtype == dtype and out.shape == (h * w, c)
+        err = float((out.float() - ref).abs().max()) / float(ref.abs().max())
+        assert err <= tol, (n_terms, err)
+    lin = ops.upsample_sum(terms[:2], (h, w))                           # no bias, no activation
+    ref = terms[0].float().reshape(h * w, c) + F.interpolate(terms[1].float().permute(2, 0, 1).unsqueeze(0), (h, w), mode="bilinear",
+                                                             align_corners=True)[0].permute(1, 2, 0).reshape(h * w, c)
+    assert float((lin.float() - ref).abs().max()) / float(ref.abs().max()) <= tol
+
+
+@pytest.mark.parametrize("hc_dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_pixel_model_without_hypercolumn_equals_the_reference_order_of_operations(hc_dtype, tol):
+    """project_first (GEMMs at the levels' resolution + upsample_sum) against the reference's order (hypercolumn, then
+    the 2112-wide Linear) through the same weights, and against the oracle's dense formulation in fp32."""
+    from oracle import wesup_ref as O
+    torch.backends.cudnn.allow_tf32 = False            # the side convolutions of the reference order would otherwise run in TF32
+    torch.manual_seed(3)
+    model = WESUPPixelInference(pretrained=False, hc_dtype=hc_dtype).to(DEV).eval()
+    O.seeded_init_(model, seed=9)
+    classic = WESUPPixelInference(pretrained=False, hc_dtype=hc_dtype, project_first=False).to(DEV).eval()
+    classic.load_state_dict(model.state_dict())
+    x = synth.to_tensor(synth.he_like_image(75, 94, seed=4)[0]).unsqueeze(0).to(DEV)       # floor-division level sizes
+    with torch.no_grad():
+        a, b = model(x), classic(x)
+        ref = O.seeded_init_(O.RefWESUP(), seed=9).forward_pixels(x.cpu())
+    assert a.shape == (75, 94, 2) and model.feature_maps is None
+    assert float((a - b).abs().max()) <= tol
+    assert float((a.cpu() - ref).abs().max()) <= tol
+    xb = torch.cat([x, x.flip(-1)])
+    with torch.no_grad():
+        ab = model.forward_batch(xb)
+    assert float((ab[0] - a).abs().max()) <= tol and float((ab[1] - model(x.flip(-1))).abs().max()) <= tol
+    torch.backends.cudnn.allow_tf32 = True

@@ -53,6 +53,7 @@ SIGNATURES = {
     "wesup_label_propagate_tc": (c_int, [_vp, c_int, c_int, c_int, _vp, c_int, c_float, _vp, _vp, _vp, _vp, _vp]),
     "wesup_label_propagate_tc_stats": (c_int, [_vp, c_int, c_int, POINTER(ctypes.c_ulonglong)]),
     "wesup_label_propagate_dev": (c_int, [_vp, c_int, c_int, _vp, _vp, c_int, c_float, _vp, _vp]),
+    "wesup_upsample_sum": (c_int, [POINTER(_vp), _ip, _ip, c_int, c_int, c_int, c_int, c_int, _vp, c_int, _vp, _vp]),
     "wesup_slic_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "wesup_slic": (c_int, [_vp, c_int, c_int, c_int, c_int, c_double, c_int, c_int, _vp, _vp, _vp, _vp]),
     "wesup_slic_batch_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

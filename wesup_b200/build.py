@@ -18,7 +18,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "csrc" / "_obj"
 LIB = PKG / "libwesup_b200.so"
-SOURCES = ["abi.cu", "hypercolumn.cu", "sp_pool.cu", "label_propagate.cu", "label_propagate_tc.cu", "slic.cu", "fused_bwd.cu", "fused_fwd.cu", "pool_levels.cu", "footprint.cu", "colsum.cu"]
+SOURCES = ["abi.cu", "hypercolumn.cu", "sp_pool.cu", "label_propagate.cu", "label_propagate_tc.cu", "slic.cu", "fused_bwd.cu", "fused_fwd.cu", "pool_levels.cu", "footprint.cu", "colsum.cu", "upsample_sum.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

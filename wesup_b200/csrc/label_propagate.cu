@@ -185,7 +185,7 @@ static long tc_min_pairs() {
     static long v = -1;
     if (v < 0) {
         const char *e = getenv("WESUP_LP_TC_MIN_PAIRS");
-        v = e ? atol(e) : 16384;
+        v = e ? atol(e) : (1L << 21);
         if (v < 0) v = 0;
     }
     return v;

@@ -130,7 +130,7 @@ class BaseTrainer(ABC):
     def _run_iteration(self, phase, input_, target):
         """Everything of `train_one_iteration` after `preprocess`."""
         if self.grad_sync is not None:
-            self.grad_sync.zero_grad()       # keeps .grad as views of the flat all-reduce buffer
+            self.grad_sync.zero_grad()       # drops the gradients and resets the bucket arrival counters
         else:
             self.optimizer.zero_grad()
         metrics = {}

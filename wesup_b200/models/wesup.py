@@ -284,35 +284,87 @@ class WESUPPixelInference(WESUP):
         super().__init__(n_classes=n_classes, D=D, **kwargs)
 
     def forward(self, x):
-        height, width = x.size()[-2:]
-        feats = self._hypercolumn(x)
-        if feats.dtype == torch.bfloat16:
-            # bf16 hypercolumn => the (H*W,2112)@(2112,1024) GEMM chain runs on the bf16 tensor
-            # cores straight from the tensor kernel (a) wrote (no fp32 copy); softmax in fp32.
-            # Opt-in (hc_dtype=torch.bfloat16): 1e-2 relative, the north star's bf16 tolerance.
-            with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
-                logits = self.classifier[0](self.fc_layers(feats))
-            out = torch.softmax(logits.float(), dim=1)
-        else:
-            out = self.classifier(self.fc_layers(feats))
-        return out.view(height, width, -1)
+        """x (1,3,H,W) -> (H,W,C) class probabilities (reference :382-400)."""
+        return self.forward_batch(x)[0]
+
+    def _backbone_levels(self, x):
+        """The 13 PRE-ReLU backbone conv outputs (channels_last), what the reference's hooks see (:205-210)."""
+        x = x.contiguous(memory_format=torch.channels_last)
+        outs = []
+        for layer in self.backbone:
+            if isinstance(layer, nn.Conv2d):
+                x = layer(x)
+                outs.append(x)
+            elif isinstance(layer, nn.ReLU):
+                x = F.relu(x)
+            else:
+                x = layer(x)
+        return outs
+
+    def _folded_first_layer(self, outs, dtype):
+        """Per distinct level resolution g: W'_g = cat_{l in g}(W1[:, slice_l] @ Wside_l)  (1024, sum of the backbone
+        channels of the resolution), and the total bias b' = b1 + sum_l W1[:, slice_l] @ bside_l.  Recomputed from the
+        current parameters on every call (13 small GEMMs, < 1 GFLOP), so it can never go stale."""
+        w1, b1 = self.fc_layers[0].weight, self.fc_layers[0].bias
+        groups, bias, off = [], b1.float(), 0
+        for name, o in zip(self._side_names, outs):
+            conv = getattr(self, name)
+            half = conv.out_channels
+            w1_l = w1[:, off:off + half].float()
+            folded = w1_l @ conv.weight.view(half, conv.in_channels).float()          # (1024, C_l)
+            bias = bias + w1_l @ conv.bias.float()
+            size = (o.size(2), o.size(3))
+            if groups and groups[-1][0] == size:
+                groups[-1][1].append(folded)
+                groups[-1][2].append(o)
+            else:
+                groups.append((size, [folded], [o]))
+            off += half
+        return [(size, torch.cat(ws, dim=1).to(dtype), lv) for size, ws, lv in groups], bias
 
     def forward_batch(self, x):
-        """`forward` for a batch of same-sized tiles `(B,3,H,W)` -> `(B,H,W,C)`: VGG16 and the side convolutions run
-        once at batch size B, the hypercolumn kernel once per tile, the MLP on all B*H*W rows at once."""
+        """`forward` for a batch of same-sized tiles `(B,3,H,W)` -> `(B,H,W,C)`.  The first MLP layer is taken through
+        the linear chain side conv -> upsample -> concat -> Linear(2112,1024) analytically (csrc/upsample_sum.cu): one
+        library GEMM per level resolution on (B*h*w, C) rows, then ONE kernel per tile that upsamples, sums, adds the
+        bias and applies the ReLU -- the (H*W,2112) hypercolumn is never formed and the layer costs 88 GFLOP per
+        400-px tile instead of 692.  `project_first=False` keeps the reference's order of operations
+        (hypercolumn kernel, then the 2112-wide GEMM)."""
         b, _, height, width = x.shape
         self.fm_size = (height, width)
-        sides = self._side_outputs(x)
         hw = height * width
-        feats = torch.empty((b * hw, self.fm_channels_sum), dtype=self.hc_dtype, device=x.device)
-        for t in range(b):
-            ops.hypercolumn_into([s[t:t + 1] for s in sides], self.fm_size, feats[t * hw:(t + 1) * hw])
-        if feats.dtype == torch.bfloat16:
-            with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
-                logits = self.classifier[0](self.fc_layers(feats))
+        if not bool(self.kwargs.get("project_first", True)):
+            sides = self._side_outputs(x)
+            feats = torch.empty((b * hw, self.fm_channels_sum), dtype=self.hc_dtype, device=x.device)
+            for t in range(b):
+                ops.hypercolumn_into([s[t:t + 1] for s in sides], self.fm_size, feats[t * hw:(t + 1) * hw])
+            self.feature_maps = feats.t().view(-1, height, width) if b == 1 else None
+            h1, rest = feats, self.fc_layers
+        else:
+            self.feature_maps = None
+            outs = self._backbone_levels(x)
+            dtype = self.hc_dtype
+            groups, bias = self._folded_first_layer(outs, dtype)
+            terms = []
+            for (gh, gw), w_g, levels in groups:
+                rows = torch.empty((b * gh * gw, w_g.size(1)), dtype=dtype, device=x.device)
+                off = 0
+                for o in levels:                                        # (B,C,h,w) channels_last == (B*h*w, C) rows: one converting copy
+                    rows[:, off:off + o.size(1)].copy_(o.permute(0, 2, 3, 1).reshape(-1, o.size(1)))
+                    off += o.size(1)
+                terms.append(F.linear(rows, w_g).view(b, gh, gw, -1))   # Z_g at the level's own resolution
+            h1 = torch.empty((b * hw, terms[0].size(-1)), dtype=dtype, device=x.device)
+            for t in range(b):
+                ops.upsample_sum([z[t] for z in terms], self.fm_size, bias=bias, relu=True, out=h1[t * hw:(t + 1) * hw])
+            rest = self.fc_layers[2:]
+        if h1.dtype == torch.bfloat16:
+            # bf16 tensor-core GEMMs with the bias + ReLU in the GEMM epilogue (cuBLASLt), softmax in fp32
+            for layer in rest:
+                if isinstance(layer, nn.Linear):
+                    h1 = torch._addmm_activation(layer.bias.to(torch.bfloat16), h1, layer.weight.to(torch.bfloat16).t())
+            logits = F.linear(h1, self.classifier[0].weight.to(torch.bfloat16), self.classifier[0].bias.to(torch.bfloat16))
             out = torch.softmax(logits.float(), dim=1)
         else:
-            out = self.classifier(self.fc_layers(feats))
+            out = self.classifier(rest(h1))
         return out.view(b, height, width, -1)
 
 
@@ -527,8 +579,7 @@ class WESUPTrainer(BaseTrainer):
             if self.grad_sync is not None:
                 self.grad_sync.suspended = False
         torch.cuda.current_stream(dev).wait_stream(side)
-        if self.grad_sync is None:
-            self.optimizer.zero_grad(set_to_none=True)
+        self.optimizer.zero_grad(set_to_none=True)
         graph = torch.cuda.CUDAGraph()
         lib = ops._lib.load()
         n0 = lib.wesup_kernel_launches()

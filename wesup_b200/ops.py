@@ -722,6 +722,30 @@ def hypercolumn_into(sides: Sequence[torch.Tensor], size: Tuple[int, int], out: 
           out.data_ptr(), _DTYPES[out.dtype], HWC)
 
 
+def upsample_sum(terms: Sequence[torch.Tensor], size: Tuple[int, int], bias: Optional[torch.Tensor] = None, relu: bool = False,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[p,:] = act(bias + sum_g bilinear(align_corners=True)(terms[g])[p,:]) -> (H*W, C) (forward only).
+    `terms`: pixel-major (h_g, w_g, C) tensors of one dtype (fp32 or bf16), at most 5; a term of size (H, W) is
+    added as it is.  See csrc/upsample_sum.cu: with terms = per-resolution products of the backbone levels with the
+    folded first-layer weights this is ReLU(Linear1(hypercolumn)) of the pixel-wise model without the hypercolumn."""
+    H, W = int(size[0]), int(size[1])
+    t0 = terms[0]
+    _require_cuda(t0, "terms")
+    C = t0.size(-1)
+    for t in terms:
+        if t.dim() != 3 or t.size(-1) != C or t.dtype != t0.dtype or not t.is_contiguous():
+            raise ValueError("terms must be contiguous (h, w, C) tensors of one dtype and channel count")
+    if out is None:
+        out = torch.empty((H * W, C), dtype=t0.dtype, device=t0.device)
+    elif out.shape != (H * W, C) or out.dtype != t0.dtype or not out.is_contiguous():
+        raise ValueError("out must be a contiguous (H*W, C) tensor of the terms' dtype")
+    b = None if bias is None else bias.detach().float().contiguous()
+    _call("wesup_upsample_sum", out, _lib.ptr_array([t.data_ptr() for t in terms]), _lib.int_array([t.size(0) for t in terms]),
+          _lib.int_array([t.size(1) for t in terms]), len(terms), H, W, C, _DTYPES[t0.dtype], None if b is None else b.data_ptr(),
+          int(bool(relu)), out.data_ptr())
+    return out
+
+
 def paint_into(sp: SuperpixelMaps, sp_pred: torch.Tensor, out: torch.Tensor, cls: int = 1) -> None:
     """`paint` into a caller-owned fp32 (H,W) buffer."""
     _call("wesup_sp_paint", out, sp.row_labels.data_ptr(), sp_pred.data_ptr(), sp.height * sp.width, sp_pred.size(1), cls,
