@@ -400,7 +400,7 @@ def label_propagation_kernels(dev, flush, lib, shapes, out):
             entry = {"ms": ms, "n": n, "n_l": n_l, "useful_flops": 2.0 * n_u * n_l * 32,
                      "useful_tflops": 2.0 * n_u * n_l * 32 / ms / 1e9}
             if algo == "tc":
-                entry["tensor_flops"] = 2.0 * n_u * n_l * 96           # split-TF32: K' = 3 * 32
+                entry["tensor_flops"] = 2.0 * n_u * n_l * 104          # split-TF32: 13 MMAs of K = 8 (hi.hi, hi.lo, lo.hi, norm step)
                 entry["tensor_tflops"] = entry["tensor_flops"] / ms / 1e9
                 st_ = ops.label_propagate(f, y_l, 0.8, algo="tc", return_stats=True)[-1]
                 entry["exact_reevaluations_per_row"] = st_["exact_evals"] / max(n_u, 1)

@@ -197,9 +197,9 @@ int wesup_sp_paint(const int32_t *row_labels, const float *sp_pred, int HW, int 
  * src = first arg-max, y_u[u] = y_l[src] iff sim > thr (strict) else 0.
  * y_u (N-n_l,n_cls); src_idx, max_sim (N-n_l) may be NULL. */
 size_t wesup_label_propagate_workspace_bytes(int N, int D, int n_l);
-/* dispatcher: the tcgen05 path when D == 32 and n_u*n_l is large enough to fill
- * the tensor pipe (WESUP_LP_TC_MIN_PAIRS, default 16384), else the CUDA-core
- * path; both give bit-identical src_idx / max_sim / y_u. */
+/* dispatcher: the tcgen05 path when D == 32 and there are at least
+ * WESUP_LP_TC_MIN_LABELED (default 64, the measured crossover) labeled rows,
+ * else the CUDA-core path; both give bit-identical src_idx / max_sim / y_u. */
 int wesup_label_propagate(const float *feats, int N, int D, int n_l, const float *y_l, int n_cls,
                           float thr, float *y_u, int32_t *src_idx, float *max_sim, void *ws,
                           void *stream);

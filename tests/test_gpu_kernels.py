@@ -429,6 +429,15 @@ def test_precomputed_footprint_pooling_matches_the_in_kernel_footprint_kernels(h
         os.environ.pop("WESUP_FP_BWD")
     for x, y in zip(gc, ga):
         assert torch.isfinite(x).all() and rel_err(x, y) < tol
+    os.environ["WESUP_FP_BWD"] = "split"                     # default = one merged launch; "split" = cells + identity kernels
+    try:
+        gs = [torch.full_like(s, float("nan")) for s in sides]
+        _levels_call("wesup_levels_pool_bwd_fp", gp.data_ptr(), sp.row_labels.data_ptr(), counts.data_ptr(), ca, ha, wa, nl, h, w,
+                     cap, fp.data_ptr(), _lib.ptr_array([t.data_ptr() for t in gs]), st)
+    finally:
+        os.environ.pop("WESUP_FP_BWD")
+    for x, y in zip(gs, ga):
+        assert torch.equal(x, y)                             # same arithmetic per element, only the launch shape differs
     lhs = (a.double() * gp.double()).sum()
     rhs = sum((s_.double() * g.double()).sum() for s_, g in zip(sides, ga))
     scale = float((a.double() * gp.double()).abs().sum())

@@ -46,10 +46,18 @@ def main():
         ms = bench.time_kernel(fn, 20, flush)
         return {"ms": ms, "gbs": nbytes / ms / 1e6}
 
+    import os
     out["fwd"] = timed(fwd)
     out["bwd"] = timed(bwd)
+    merged = [t.clone() for t in gl]
+    os.environ["WESUP_FP_BWD"] = "split"              # cells + identity kernels as two launches on two streams
+    for t in gl:
+        t.zero_()
+    out["bwd_split_launches"] = timed(bwd)
+    os.environ.pop("WESUP_FP_BWD")
+    torch.cuda.synchronize()
+    out["bwd_merged_equals_split"] = all(torch.equal(a, b) for a, b in zip(merged, gl))
     if not bench.QUICK:
-        import os
         os.environ["WESUP_FP_FWD"] = "chunks"
         out["fwd_chunk_kernel"] = timed(fwd)
         os.environ.pop("WESUP_FP_FWD")

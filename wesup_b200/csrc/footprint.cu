@@ -28,6 +28,7 @@
 #include <limits.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace wesup {
 
@@ -736,9 +737,14 @@ __global__ void __launch_bounds__(FP_THREADS) fp_pool_bwd_kernel(const Levels L,
 //     8 / V entries in flight -- the forward kernel transposed.
 constexpr int BC_THREADS = 128;
 constexpr int BC_WARPS = BC_THREADS / 32;
+constexpr int BC_MAX = WESUP_MAX_LEVELS;
+constexpr int BC_SLICE = 512;            // widest channel slice a warp gathers (r2 measurements: halving it to 256 -- 64
+                                         // registers, eight blocks per SM -- LOST 10 %: the piece size of the gathers matters
+                                         // more than the occupancy, as in the forward kernel)
 struct BwdCellsPlan {
-    int n;                               // levels handled here
-    int lvl[WESUP_MAX_LEVELS], res[WESUP_MAX_LEVELS], batch[WESUP_MAX_LEVELS], blk0[WESUP_MAX_LEVELS + 1];
+    int n;                               // (level, channel slice) pairs handled here
+    short lvl[BC_MAX], res[BC_MAX], batch[BC_MAX], choff[BC_MAX], cw[BC_MAX];
+    int blk0[BC_MAX + 1];
 };
 
 template <int V, int EPRE, int CU>
@@ -835,45 +841,50 @@ __device__ __forceinline__ void bc_cell(const float *__restrict__ gpl, int Ctot,
     for (int qv = 0; qv < V; ++qv) stg_stream(o + 32 * qv, acc[qv]);
 }
 
+// one warp unit of the cell lists: `wunit` counts 32-cell batches (fine levels) or single cells (coarse levels) of entry i
+__device__ __forceinline__ void bc_unit(const Levels &L, const FpPlan &P, const BwdCellsPlan &B, const float *__restrict__ gp, int i,
+                                        int wunit, int lane) {
+    const int l = B.lvl[i];
+    const FpRes &R = P.r[B.res[i]];
+    const int cells = R.h * R.w;
+    const int Cl = L.C[l], Ctot = L.Ctot, cw = B.cw[i];
+    const float *__restrict__ gpl = gp + L.coff[l] + B.choff[i] + lane * 4;
+    float *__restrict__ dst = L.dst[l] + B.choff[i] + lane * 4;
+    if (B.batch[i]) {
+        const int q0 = wunit * 32;
+        if (q0 >= cells) return;
+        if (cw == 128) bc_batch<1, 2, 4>(gpl, Ctot, dst, Cl, R, q0, cells, lane);
+        else if (cw == 256) bc_batch<2, 2, 2>(gpl, Ctot, dst, Cl, R, q0, cells, lane);
+        else bc_batch<4, 2, 1>(gpl, Ctot, dst, Cl, R, q0, cells, lane);
+    } else {
+        if (wunit >= cells) return;
+        if (cw == 128) bc_cell<1>(gpl, Ctot, dst, Cl, R, wunit, lane);
+        else if (cw == 256) bc_cell<2>(gpl, Ctot, dst, Cl, R, wunit, lane);
+        else bc_cell<4>(gpl, Ctot, dst, Cl, R, wunit, lane);
+    }
+}
+
 __global__ void __launch_bounds__(BC_THREADS, 6) fp_pool_bwd_cells_kernel(const Levels L, const FpPlan P, const BwdCellsPlan B,
                                                                           const float *__restrict__ gp) {
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int i = 0;
     while (i + 1 < B.n && (int)blockIdx.x >= B.blk0[i + 1]) ++i;
-    const int l = B.lvl[i];
-    const FpRes &R = P.r[B.res[i]];
-    const int cells = R.h * R.w;
-    const int Cl = L.C[l], Ctot = L.Ctot;
-    const float *__restrict__ gpl = gp + L.coff[l] + lane * 4;
-    float *__restrict__ dst = L.dst[l] + lane * 4;
-    const int wunit = ((int)blockIdx.x - B.blk0[i]) * BC_WARPS + wid;
-    if (B.batch[i]) {
-        const int q0 = wunit * 32;
-        if (q0 >= cells) return;
-        if (Cl == 128) bc_batch<1, 2, 4>(gpl, Ctot, dst, Cl, R, q0, cells, lane);
-        else if (Cl == 256) bc_batch<2, 2, 2>(gpl, Ctot, dst, Cl, R, q0, cells, lane);
-        else bc_batch<4, 2, 1>(gpl, Ctot, dst, Cl, R, q0, cells, lane);
-    } else {
-        if (wunit >= cells) return;
-        if (Cl == 128) bc_cell<1>(gpl, Ctot, dst, Cl, R, wunit, lane);
-        else if (Cl == 256) bc_cell<2>(gpl, Ctot, dst, Cl, R, wunit, lane);
-        else bc_cell<4>(gpl, Ctot, dst, Cl, R, wunit, lane);
-    }
+    bc_unit(L, P, B, gp, i, ((int)blockIdx.x - B.blk0[i]) * BC_WARPS + wid, lane);
 }
 
 // full-resolution levels: grad[p, c] = grad_pooled[row(p), c] / |S_row(p)|.  A warp takes 32 consecutive pixels: label and
 // 1/|S| of pixel p0 + lane are loaded once, lane-parallel, and broadcast with shuffles; the pooled-gradient row
 // (L2-resident) is re-fetched only when the label changes along the run (a superpixel is ~14 pixels wide), so the
 // steady state is shuffle, shuffle, four multiplies, one 128-bit streaming store per pixel.
-__global__ void __launch_bounds__(256) fp_pool_bwd_ident_kernel(const Levels L, const PoolGroup bg, const float *__restrict__ gp,
-                                                                const int32_t *__restrict__ row_labels,
-                                                                const int32_t *__restrict__ counts, long HW) {
-    const int lane = threadIdx.x & 31;
-    const long p0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
-    if (p0 >= HW) return;
+// One warp, 32 consecutive pixels.  The pixels are walked eight at a time: the (warp-uniform) loads of the rows whose label
+// differs from the previous pixel's are issued together, the others reuse the previous value, then eight stores follow.
+__device__ __forceinline__ void ident_unit(const Levels &L, const PoolGroup &bg, const float *__restrict__ gp,
+                                           const int32_t *__restrict__ row_labels, const int32_t *__restrict__ counts, long HW, long p0,
+                                           int lane) {
+    constexpr int PU = 8;
     const int nch4 = bg.Cg >> 2, Ctot = L.Ctot;
     const int np = (int)min(32L, HW - p0);
-    int my_lab = -1;
+    int my_lab = 0;
     float my_scale = 0.f;
     if (lane < np) {
         my_lab = __ldg(row_labels + p0 + lane);
@@ -887,19 +898,74 @@ __global__ void __launch_bounds__(256) fp_pool_bwd_ident_kernel(const Levels L, 
         if (live) locate_level(L, bg.l0, bg.l1, c4 << 2, l, cl);
         const int Cl = L.C[l];
         float *__restrict__ dst = L.dst[l] + cl + p0 * Cl;
-        const float *__restrict__ src = gp + bg.coff + (c4 << 2);
+        const float *__restrict__ src = gp + bg.coff + (live ? (c4 << 2) : 0);
         int prev = -1;
         float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = 0; i < np; ++i) {
-            const int lab = __shfl_sync(0xffffffffu, my_lab, i);
-            const float sc = __shfl_sync(0xffffffffu, my_scale, i);
-            if (lab != prev) {                              // warp-uniform
-                if (live) val = __ldg(reinterpret_cast<const float4 *>(src + (long)lab * Ctot));
-                prev = lab;
+        for (int i0 = 0; i0 < np; i0 += PU) {
+            int lab[PU];
+            float sc[PU];
+            float4 v[PU];
+#pragma unroll
+            for (int t = 0; t < PU; ++t) {
+                lab[t] = __shfl_sync(0xffffffffu, my_lab, (i0 + t) & 31);
+                sc[t] = __shfl_sync(0xffffffffu, my_scale, (i0 + t) & 31);
             }
-            if (live) stg_stream(reinterpret_cast<float4 *>(dst + (long)i * Cl), sc * val);
+#pragma unroll
+            for (int t = 0; t < PU; ++t) {
+                const bool fresh = lab[t] != (t == 0 ? prev : lab[t - 1]);      // warp-uniform
+                v[t] = val;
+                if (fresh) v[t] = __ldg(reinterpret_cast<const float4 *>(src + (long)lab[t] * Ctot));
+            }
+#pragma unroll
+            for (int t = 0; t < PU; ++t) {
+                const bool fresh = lab[t] != (t == 0 ? prev : lab[t - 1]);
+                if (!fresh) v[t] = t == 0 ? val : v[t - 1];
+                if (live && i0 + t < np) stg_stream(reinterpret_cast<float4 *>(dst + (long)(i0 + t) * Cl), sc[t] * v[t]);
+            }
+            prev = lab[PU - 1];
+            val = v[PU - 1];
         }
     }
+}
+
+__global__ void __launch_bounds__(256) fp_pool_bwd_ident_kernel(const Levels L, const PoolGroup bg, const float *__restrict__ gp,
+                                                                const int32_t *__restrict__ row_labels,
+                                                                const int32_t *__restrict__ counts, long HW) {
+    const long p0 = ((long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+    if (p0 >= HW) return;
+    ident_unit(L, bg, gp, row_labels, counts, HW, p0, threadIdx.x & 31);
+}
+
+// Both kinds of work in ONE launch (default).  As two launches on two streams the write stream of the identity levels
+// and the latency-bound list gathers did not overlap: a full wave of either kernel owns the register file.  Here the
+// block index decides the role, identity blocks spread evenly between the list blocks (coarse levels first), so both are
+// resident on every SM at all times.
+struct BwdAllPlan { int ident_blocks, total_blocks, order; };
+template <int MINB>
+__global__ void __launch_bounds__(BC_THREADS, MINB) fp_pool_bwd_all_kernel(const Levels L, const FpPlan P, const BwdCellsPlan B,
+                                                                        const PoolGroup ig, const BwdAllPlan A,
+                                                                        const float *__restrict__ gp,
+                                                                        const int32_t *__restrict__ row_labels,
+                                                                        const int32_t *__restrict__ counts, long HW) {
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long b = blockIdx.x;
+    int before;                                                                 // identity blocks among [0, b)
+    bool is_ident;
+    if (A.order == 1) { is_ident = b < A.ident_blocks; before = is_ident ? (int)b : A.ident_blocks; }
+    else if (A.order == 2) { const int nc_ = A.total_blocks - A.ident_blocks; is_ident = b >= nc_; before = is_ident ? (int)b - nc_ : 0; }
+    else {
+        before = (int)(b * A.ident_blocks / A.total_blocks);
+        is_ident = (int)((b + 1) * A.ident_blocks / A.total_blocks) > before;
+    }
+    if (is_ident) {
+        const long p0 = ((long)before * BC_WARPS + wid) * 32;
+        if (p0 < HW) ident_unit(L, ig, gp, row_labels, counts, HW, p0, lane);
+        return;
+    }
+    const int cb = (int)b - before;
+    int i = 0;
+    while (i + 1 < B.n && cb >= B.blk0[i + 1]) ++i;
+    bc_unit(L, P, B, gp, i, (cb - B.blk0[i]) * BC_WARPS + wid, lane);
 }
 
 // ---------------------------------------------------------------------------
@@ -1078,7 +1144,11 @@ extern "C" int wesup_levels_pool_bwd_fp(const float *grad_pooled, const int32_t 
     // non-identity levels of 128 / 256 / 512 channels: whole cells per warp, coarse levels (long lists) first; a group
     // with any other channel count (and WESUP_FP_BWD=chunks, the cross-check of the tests) takes the chunk kernel
     const double side = sqrt((double)H * W / (double)N);
-    const bool force_chunks = getenv("WESUP_FP_BWD") != nullptr;
+    const char *force_env = getenv("WESUP_FP_BWD");                 // "chunks": chunk kernel (cross-check); "split": separate launches
+    const bool force_chunks = force_env && strcmp(force_env, "chunks") == 0;
+    // experiment knobs (WESUP_FP_X="order,minb")
+    int x_order = 0, x_minb = 6;
+    if (const char *x = getenv("WESUP_FP_X")) sscanf(x, "%d,%d", &x_order, &x_minb);
     BwdCellsPlan BC;
     BC.n = 0;
     long cblocks = 0;
@@ -1095,11 +1165,14 @@ extern "C" int wesup_levels_pool_bwd_fp(const float *grad_pooled, const int32_t 
         const double fy = R.sy > 0.f ? 2.0 / R.sy : (double)H, fx = R.sx > 0.f ? 2.0 / R.sx : (double)W;
         const bool batch = (fy / side + 1.0) * (fx / side + 1.0) < 3.5;
         for (int l = G.g[g].l0; l < G.g[g].l1; ++l) {
-            const int i = BC.n++;
-            BC.lvl[i] = l; BC.res[i] = G.g[g].res; BC.batch[i] = batch ? 1 : 0;
-            BC.blk0[i] = (int)cblocks;
-            const long cells = (long)R.h * R.w;
-            cblocks += cdiv(batch ? cdiv(cells, 32) : cells, BC_WARPS);
+            for (int off = 0; off < L.C[l]; off += BC_SLICE) {
+                const int i = BC.n++;
+                BC.lvl[i] = (short)l; BC.res[i] = (short)G.g[g].res; BC.batch[i] = batch ? 1 : 0;
+                BC.choff[i] = (short)off; BC.cw[i] = (short)min(BC_SLICE, L.C[l] - off);
+                BC.blk0[i] = (int)cblocks;
+                const long cells = (long)R.h * R.w;
+                cblocks += cdiv(batch ? cdiv(cells, 32) : cells, BC_WARPS);
+            }
         }
     }
     BC.blk0[BC.n] = (int)cblocks;
@@ -1115,16 +1188,29 @@ extern "C" int wesup_levels_pool_bwd_fp(const float *grad_pooled, const int32_t 
         S.blk0 = blocks;
         blocks += cdiv((long)P.r[S.res].h * P.r[S.res].w * S.nchunk, FP_WARPS);
     }
-    // the identity groups (a pure write stream) run beside the list kernel (latency-bound gathers) on the library's
-    // auxiliary stream: event dependencies only, which also capture into a CUDA graph as parallel branches
-    bool any_ident = false;
-    for (int g = 0; g < G.n; ++g) any_ident = any_ident || G.g[g].res < 0;
+    const long HW = (long)H * W;
+    int n_ident = 0, g_ident = -1;
+    for (int g = 0; g < G.n; ++g)
+        if (G.g[g].res < 0) { ++n_ident; g_ident = g; }
+    // default: one launch, identity blocks spread between the list blocks (WESUP_FP_BWD=split|chunks: the separate kernels)
+    const long iblocks = cdiv(cdiv(HW, 32), BC_WARPS);
+    if (!force_env && n_ident == 1 && BC.n > 0 && B.n == 0 && iblocks + cblocks < (1L << 30)) {
+        BwdAllPlan A;
+        A.ident_blocks = (int)iblocks; A.total_blocks = (int)(iblocks + cblocks);
+        A.order = x_order;
+        if (x_minb == 8)
+            fp_pool_bwd_all_kernel<8><<<A.total_blocks, BC_THREADS, 0, stream>>>(L, P, BC, G.g[g_ident], A, grad_pooled, row_labels, counts, HW);
+        else
+            fp_pool_bwd_all_kernel<6><<<A.total_blocks, BC_THREADS, 0, stream>>>(L, P, BC, G.g[g_ident], A, grad_pooled, row_labels, counts, HW);
+        WESUP_CHECK_LAUNCH("wesup_levels_pool_bwd_fp", 1);
+        return 0;
+    }
+    // separate kernels: the identity groups on the library's auxiliary stream (event dependencies only, which also
+    // capture into a CUDA graph as parallel branches)
     cudaStream_t s_ident = stream;
-    AuxStream *aux = ((B.n > 0 || BC.n > 0) && any_ident) ? aux_stream() : nullptr;
+    AuxStream *aux = ((B.n > 0 || BC.n > 0) && n_ident > 0) ? aux_stream() : nullptr;
     if (aux && cudaEventRecord(aux->fork, stream) == cudaSuccess && cudaStreamWaitEvent(aux->s, aux->fork, 0) == cudaSuccess)
         s_ident = aux->s;
-    // the identity launch goes first: its 1 wave of short blocks leaves room for the list kernels to start beside it
-    const long HW = (long)H * W;
     for (int g = 0; g < G.n; ++g) {
         if (G.g[g].res >= 0) continue;
         fp_pool_bwd_ident_kernel<<<cdiv(cdiv(HW, 32), 8), 256, 0, s_ident>>>(L, G.g[g], grad_pooled, row_labels, counts, HW);

@@ -179,14 +179,15 @@ extern "C" size_t wesup_label_propagate_tc_workspace_bytes(int N, int D, int n_l
 extern "C" int wesup_label_propagate_tc(const float *feats, int N, int D, int n_l, const float *y_l, int n_cls, float thr,
                                         float *y_u, int32_t *src_idx, float *max_sim, void *ws, void *stream_);
 
-// Pairs (n_u * n_l) from which the tensor-core path is taken; below it the whole
-// problem is a handful of CTAs and the single-launch CUDA-core kernel wins on latency.
-static long tc_min_pairs() {
+// Labeled rows from which the tensor-core path is taken.  Measured on B200 (profiles/r2d_bench_lp.txt): the CUDA-core
+// kernel costs ~10 us + 0.14 us per labeled row (every unlabeled row walks all of them), the tcgen05 pipeline ~15 us
+// flat up to a few thousand rows each way -- the crossover is near 40 labeled rows.
+static long tc_min_labeled() {
     static long v = -1;
     if (v < 0) {
-        const char *e = getenv("WESUP_LP_TC_MIN_PAIRS");
-        v = e ? atol(e) : (1L << 21);
-        if (v < 0) v = 0;
+        const char *e = getenv("WESUP_LP_TC_MIN_LABELED");
+        v = e ? atol(e) : 64;
+        if (v < 1) v = 1;
     }
     return v;
 }
@@ -202,7 +203,7 @@ extern "C" int wesup_label_propagate_exact(const float *feats, int N, int D, int
 extern "C" int wesup_label_propagate(const float *feats, int N, int D, int n_l, const float *y_l, int n_cls, float thr,
                                      float *y_u, int32_t *src_idx, float *max_sim, void *ws, void *stream_) {
     if (feats && ws && D == 32 && n_l > 0 && n_l < N && aligned16(feats) && aligned16(ws) &&
-        (long)(N - n_l) * n_l >= tc_min_pairs())
+        n_l >= tc_min_labeled())
         return wesup_label_propagate_tc(feats, N, D, n_l, y_l, n_cls, thr, y_u, src_idx, max_sim, ws, stream_);
     return wesup_label_propagate_exact(feats, N, D, n_l, y_l, n_cls, thr, y_u, src_idx, max_sim, ws, stream_);
 }

@@ -20,13 +20,6 @@ namespace wesup {
 
 constexpr int UPS_MAX_GROUPS = 5;
 
-struct UpsGroups {
-    const void *src[UPS_MAX_GROUPS];
-    int h[UPS_MAX_GROUPS], w[UPS_MAX_GROUPS];
-    float sy[UPS_MAX_GROUPS], sx[UPS_MAX_GROUPS];
-    int n, H, W, C;
-};
-
 // A thread's channel group as it sits in memory (Raw) and as fp32 values (FVec<4>): four channels per thread, i.e.
 // 16-byte accesses for fp32 and 8-byte accesses for bf16 -- the narrower bf16 group keeps the register footprint of a
 // thread (blended columns of four terms + one column of raw prefetch per term + eight pixels of the streamed term)
@@ -67,139 +60,147 @@ template <> struct Raw<__nv_bfloat16> {
 
 constexpr int UPS_V = 4;             // channels per thread
 constexpr int UPS_LOW = 4;           // low-resolution terms (plus at most one full-resolution term)
-
 constexpr int UPS_SEG = 64;          // output pixels per block (one row segment)
+constexpr int UPS_PX = 4;            // pixels per batch of the streamed (full-resolution) term
 
-template <typename T>
-__global__ void __launch_bounds__(256, 2) upsample_sum_kernel(const UpsGroups G, const float *__restrict__ bias, int relu,
+struct UpsPlan {                     // low-resolution terms first (slot order), the full-resolution term apart
+    const void *low[UPS_LOW];
+    int h[UPS_LOW], w[UPS_LOW];
+    float sy[UPS_LOW], sx[UPS_LOW];
+    const void *full;
+    int H, W, C;
+};
+
+// Instruction budget (r2 profile of the first version: 232 M warp instructions for a 400-px tile, 58 % issue-slot
+// busy, 0.2 of the HBM rate -- issue-bound, not memory-bound).  What a pixel costs a thread here:
+//   * one 128-bit + one 32-bit shared-memory load for the horizontal taps of ALL low-resolution terms (weights as a
+//     float4, "source column advances here" as a bit mask) -- computed once per block;
+//   * S0 = bias + sum_s L_s (the sum of the terms' current left columns) lives in registers, so a pixel is
+//     acc = f + S0 + sum_s w_s * D_s: one add and NLOW fused multiply-adds per channel, D_s = R_s - L_s;
+//   * an advance of term s (every 2nd / 4th / 8th / 16th pixel) costs S0 += D_s, one vertical blend of the prefetched
+//     raw column, D_s = R_new - R_old; the number of terms is a template parameter, the mask test skips the block for
+//     pixels where nothing advances.
+// S0 accumulates one rounding per advance (<= 0.5 ulp each, ~800 along a 400-px row): ~2e-6 relative, far inside the
+// 1e-4 fp32 tolerance of the tests.
+template <typename T, int NLOW>
+__global__ void __launch_bounds__(256, 2) upsample_sum_kernel(const UpsPlan G, const float *__restrict__ bias, int relu,
                                                               T *__restrict__ out) {
     typedef typename Raw<T>::type raw_t;
     constexpr int V = UPS_V;
-    constexpr int UPS_PX = 4;                                  // pixels per batch of the streamed (full-resolution) term
-    constexpr int UPS_NB = sizeof(raw_t) == 16 ? 2 : 4;        // batches in flight per thread (cp.async ring in shared memory)
+    constexpr int NB = sizeof(raw_t) == 16 ? 2 : 4;            // batches in flight per thread (cp.async ring in shared memory)
     // the streamed term never touches registers until it is used: every thread copies ITS OWN channel group of the next
-    // UPS_NB batches into its own slots with cp.async (no block synchronisation: a thread only reads what it copied), so
-    // 32 KB per block are in flight all the time instead of bursts of register loads
-    __shared__ raw_t s_full[UPS_NB * UPS_PX][256];
-    // horizontal taps of the segment, computed once per block and shared by all channel groups:
-    // {weight of column cur+1, 1 when the source column advances at this pixel}
-    __shared__ float2 s_tap[UPS_LOW][UPS_SEG];
+    // NB batches into its own slots with cp.async (no block synchronisation: a thread only reads what it copied)
+    __shared__ raw_t s_full[NB * UPS_PX][256];
+    __shared__ float4 s_w[UPS_SEG];            // weight of column cur+1 for the four slots
+    __shared__ unsigned s_adv[UPS_SEG];        // bit s: slot s moves to its next source column AT this pixel
     __shared__ int s_first[UPS_LOW];           // source column of the segment's first pixel
     const int y = blockIdx.y;
     const int x0 = blockIdx.x * UPS_SEG, x1 = min(x0 + UPS_SEG, G.W);
-    {
-        int slot = 0;
+    for (int i = threadIdx.x; i < UPS_SEG; i += blockDim.x) {
+        float wv[UPS_LOW] = {0.f, 0.f, 0.f, 0.f};
+        unsigned adv = 0u;
 #pragma unroll
-        for (int g = 0; g < UPS_MAX_GROUPS; ++g) {
-            if (g >= G.n || (G.h[g] == G.H && G.w[g] == G.W)) continue;
-            if (slot < UPS_LOW) {
-                for (int i = threadIdx.x; i < UPS_SEG; i += blockDim.x) {
-                    const Tap tx = bilinear_tap(min(x0 + i, G.W - 1), G.sx[g], G.w[g]);
-                    const int prev = i > 0 ? bilinear_tap(min(x0 + i - 1, G.W - 1), G.sx[g], G.w[g]).i0 : tx.i0;
-                    s_tap[slot][i] = make_float2(tx.w1, tx.i0 != prev ? 1.f : 0.f);
-                    if (i == 0) s_first[slot] = tx.i0;
-                }
-            }
-            ++slot;
+        for (int s = 0; s < NLOW; ++s) {
+            const Tap tx = bilinear_tap(min(x0 + i, G.W - 1), G.sx[s], G.w[s]);
+            const int prev = i > 0 ? bilinear_tap(min(x0 + i - 1, G.W - 1), G.sx[s], G.w[s]).i0 : tx.i0;
+            wv[s] = tx.w1;
+            adv |= (tx.i0 != prev ? 1u : 0u) << s;
+            if (i == 0) s_first[s] = tx.i0;
         }
+        s_w[i] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+        s_adv[i] = adv;
     }
     __syncthreads();
     const int c = threadIdx.x * V;
     if (c >= G.C) return;
     const int C = G.C;
-    FVec<V> b;
+    FVec<V> S0;                                                  // bias + sum of the slots' left columns
 #pragma unroll
-    for (int k = 0; k < V; ++k) b.v[k] = bias != nullptr ? __ldg(bias + c + k) : 0.f;
-    // the (at most one) full-resolution term is streamed, UPS_PX pixels in flight; every low-resolution term keeps its
-    // two source rows, the vertically blended column cur and the difference to column cur+1 in registers, and the RAW
-    // rows of column cur+2, requested one advance ahead of their first use so the L2 round trip overlaps the walk
-    const T *full = nullptr;
-    const T *r0[UPS_LOW], *r1[UPS_LOW];
-    float wy0[UPS_LOW], wy1[UPS_LOW];
-    int cur[UPS_LOW], wl[UPS_LOW];
-    FVec<V> c0[UPS_LOW], dc[UPS_LOW];           // column cur, and (column cur+1) - (column cur)
-    raw_t na[UPS_LOW], nb[UPS_LOW];
-    int n_low = 0;
+    for (int k = 0; k < V; ++k) S0.v[k] = bias != nullptr ? __ldg(bias + c + k) : 0.f;
+    const T *r0[NLOW > 0 ? NLOW : 1], *r1[NLOW > 0 ? NLOW : 1];
+    float wy0[NLOW > 0 ? NLOW : 1], wy1[NLOW > 0 ? NLOW : 1];
+    int nxt[NLOW > 0 ? NLOW : 1], wl[NLOW > 0 ? NLOW : 1];      // nxt: source column the raw prefetch holds (cur + 2, clamped)
+    FVec<V> R[NLOW > 0 ? NLOW : 1], D[NLOW > 0 ? NLOW : 1];      // right column (cur+1) and right - left
+    raw_t na[NLOW > 0 ? NLOW : 1], nb[NLOW > 0 ? NLOW : 1];
 #pragma unroll
-    for (int g = 0; g < UPS_MAX_GROUPS; ++g) {
-        if (g >= G.n) continue;
-        const T *src = static_cast<const T *>(G.src[g]) + c;
-        if (G.h[g] == G.H && G.w[g] == G.W) {
-            full = src + ((long)y * G.W) * C;
-            continue;
+    for (int s = 0; s < NLOW; ++s) {
+        const T *src = static_cast<const T *>(G.low[s]) + c;
+        const Tap ty = bilinear_tap(y, G.sy[s], G.h[s]);
+        r0[s] = src + (long)ty.i0 * G.w[s] * C;
+        r1[s] = src + (long)ty.i1 * G.w[s] * C;
+        wy0[s] = ty.w0; wy1[s] = ty.w1; wl[s] = G.w[s];
+        const int i0 = s_first[s];
+        const int i1 = min(i0 + 1, wl[s] - 1);
+        nxt[s] = min(i0 + 2, wl[s] - 1);
+        const FVec<V> a0 = Raw<T>::unpack(Raw<T>::load(r0[s] + (long)i0 * C)), a1 = Raw<T>::unpack(Raw<T>::load(r1[s] + (long)i0 * C));
+        const FVec<V> b0 = Raw<T>::unpack(Raw<T>::load(r0[s] + (long)i1 * C)), b1 = Raw<T>::unpack(Raw<T>::load(r1[s] + (long)i1 * C));
+        na[s] = Raw<T>::load(r0[s] + (long)nxt[s] * C);
+        nb[s] = Raw<T>::load(r1[s] + (long)nxt[s] * C);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const float L = fmaf(ty.w1, a1.v[k], ty.w0 * a0.v[k]);
+            R[s].v[k] = fmaf(ty.w1, b1.v[k], ty.w0 * b0.v[k]);
+            D[s].v[k] = R[s].v[k] - L;
+            S0.v[k] += L;
         }
-#pragma unroll
-        for (int s = 0; s < UPS_LOW; ++s) {
-            if (s != n_low) continue;                           // slot = running count of low-resolution terms
-            const Tap ty = bilinear_tap(y, G.sy[g], G.h[g]);
-            r0[s] = src + (long)ty.i0 * G.w[g] * C;
-            r1[s] = src + (long)ty.i1 * G.w[g] * C;
-            wy0[s] = ty.w0; wy1[s] = ty.w1; wl[s] = G.w[g];
-            const int i0 = s_first[s];
-            cur[s] = i0;
-            const int i1 = min(i0 + 1, wl[s] - 1), i2 = min(i0 + 2, wl[s] - 1);
-            const FVec<V> a0 = Raw<T>::unpack(Raw<T>::load(r0[s] + (long)i0 * C)), a1 = Raw<T>::unpack(Raw<T>::load(r1[s] + (long)i0 * C));
-            const FVec<V> b0 = Raw<T>::unpack(Raw<T>::load(r0[s] + (long)i1 * C)), b1 = Raw<T>::unpack(Raw<T>::load(r1[s] + (long)i1 * C));
-            na[s] = Raw<T>::load(r0[s] + (long)i2 * C);
-            nb[s] = Raw<T>::load(r1[s] + (long)i2 * C);
-#pragma unroll
-            for (int k = 0; k < V; ++k) {
-                c0[s].v[k] = fmaf(ty.w1, a1.v[k], ty.w0 * a0.v[k]);
-                dc[s].v[k] = fmaf(ty.w1, b1.v[k], ty.w0 * b0.v[k]) - c0[s].v[k];
-            }
-        }
-        ++n_low;
     }
+    const T *full = G.full != nullptr ? static_cast<const T *>(G.full) + ((long)y * G.W) * C + c : nullptr;
     T *o = out + ((long)y * G.W + x0) * C + c;
     auto issue = [&](int batch) {                                  // batch = index of a group of UPS_PX pixels of the segment
         const int xs = x0 + batch * UPS_PX;
         if (full != nullptr) {
 #pragma unroll
             for (int j = 0; j < UPS_PX; ++j)
-                if (xs + j < x1) Raw<T>::async_copy(&s_full[(batch % UPS_NB) * UPS_PX + j][threadIdx.x], full + (long)(xs + j) * C);
+                if (xs + j < x1) Raw<T>::async_copy(&s_full[(batch % NB) * UPS_PX + j][threadIdx.x], full + (long)(xs + j) * C);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 #pragma unroll
-    for (int bt = 0; bt < UPS_NB; ++bt) issue(bt);
+    for (int bt = 0; bt < NB; ++bt) issue(bt);
     int batch = 0;
     for (int xb = x0; xb < x1; xb += UPS_PX, ++batch) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(UPS_NB - 1) : "memory");      // the oldest batch has landed
+        asm volatile("cp.async.wait_group %0;" ::"n"(NB - 1) : "memory");      // the oldest batch has landed
         FVec<V> f[UPS_PX];
 #pragma unroll
         for (int j = 0; j < UPS_PX; ++j)                           // all-zero bits decode to 0 in both formats
-            f[j] = Raw<T>::unpack((full != nullptr && xb + j < x1) ? s_full[(batch % UPS_NB) * UPS_PX + j][threadIdx.x] : Raw<T>::zero());
+            f[j] = Raw<T>::unpack((full != nullptr && xb + j < x1) ? s_full[(batch % NB) * UPS_PX + j][threadIdx.x] : Raw<T>::zero());
         // refill the slots just read: the values above are in registers (unpacked), so the asynchronous writes cannot
         // overtake the reads
-        issue(batch + UPS_NB);
+        issue(batch + NB);
 #pragma unroll
         for (int j = 0; j < UPS_PX; ++j) {
             const int x = xb + j;
             if (x >= x1) break;
-            FVec<V> acc = f[j];
+            const float4 w4 = s_w[x - x0];
+            const unsigned adv = s_adv[x - x0];
+            const float wv[UPS_LOW] = {w4.x, w4.y, w4.z, w4.w};
+            if (adv != 0u) {                                        // block-uniform
 #pragma unroll
-            for (int k = 0; k < V; ++k) acc.v[k] += b.v[k];
+                for (int s = 0; s < NLOW; ++s) {
+                    if ((adv >> s) & 1u) {
+                        // an upsample advances by at most one source column per output pixel: column cur+1 becomes the
+                        // left one and the prefetched raw column (in flight since the previous advance) the right one
+                        const FVec<V> p0 = Raw<T>::unpack(na[s]), p1 = Raw<T>::unpack(nb[s]);
+                        nxt[s] = min(nxt[s] + 1, wl[s] - 1);
+                        na[s] = Raw<T>::load(r0[s] + (long)nxt[s] * C);
+                        nb[s] = Raw<T>::load(r1[s] + (long)nxt[s] * C);
 #pragma unroll
-            for (int s = 0; s < UPS_LOW; ++s) {
-                if (s >= n_low) continue;
-                const float2 tp = s_tap[s][x - x0];
-                if (tp.y != 0.f) {
-                    // an upsample advances by at most one source column per output pixel: column cur+1 becomes cur and
-                    // column cur+2 (raw, in flight since the previous advance) becomes cur+1
-                    const FVec<V> p0 = Raw<T>::unpack(na[s]), p1 = Raw<T>::unpack(nb[s]);
-                    cur[s] += 1;
-#pragma unroll
-                    for (int k = 0; k < V; ++k) {
-                        c0[s].v[k] += dc[s].v[k];
-                        dc[s].v[k] = fmaf(wy1[s], p1.v[k], wy0[s] * p0.v[k]) - c0[s].v[k];
+                        for (int k = 0; k < V; ++k) {
+                            const float rn = fmaf(wy1[s], p1.v[k], wy0[s] * p0.v[k]);
+                            S0.v[k] += D[s].v[k];
+                            D[s].v[k] = rn - R[s].v[k];
+                            R[s].v[k] = rn;
+                        }
                     }
-                    const int i2 = min(cur[s] + 2, wl[s] - 1);
-                    na[s] = Raw<T>::load(r0[s] + (long)i2 * C);
-                    nb[s] = Raw<T>::load(r1[s] + (long)i2 * C);
                 }
-#pragma unroll
-                for (int k = 0; k < V; ++k) acc.v[k] += fmaf(tp.x, dc[s].v[k], c0[s].v[k]);
             }
+            FVec<V> acc;
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc.v[k] = f[j].v[k] + S0.v[k];
+#pragma unroll
+            for (int s = 0; s < NLOW; ++s)
+#pragma unroll
+                for (int k = 0; k < V; ++k) acc.v[k] = fmaf(wv[s], D[s].v[k], acc.v[k]);
             if (relu) {
 #pragma unroll
                 for (int k = 0; k < V; ++k) acc.v[k] = fmaxf(acc.v[k], 0.f);
@@ -207,6 +208,19 @@ __global__ void __launch_bounds__(256, 2) upsample_sum_kernel(const UpsGroups G,
             st_group(o, acc);
             o += C;
         }
+    }
+}
+
+template <typename T>
+static void launch_upsample_sum(int n_low, dim3 grid, int threads, cudaStream_t stream, const UpsPlan &G, const float *bias, int relu,
+                                void *out) {
+    T *o = static_cast<T *>(out);
+    switch (n_low) {
+    case 0: upsample_sum_kernel<T, 0><<<grid, threads, 0, stream>>>(G, bias, relu, o); break;
+    case 1: upsample_sum_kernel<T, 1><<<grid, threads, 0, stream>>>(G, bias, relu, o); break;
+    case 2: upsample_sum_kernel<T, 2><<<grid, threads, 0, stream>>>(G, bias, relu, o); break;
+    case 3: upsample_sum_kernel<T, 3><<<grid, threads, 0, stream>>>(G, bias, relu, o); break;
+    default: upsample_sum_kernel<T, 4><<<grid, threads, 0, stream>>>(G, bias, relu, o); break;
     }
 }
 
@@ -227,25 +241,26 @@ extern "C" int wesup_upsample_sum(const void *const *z, const int *h, const int 
         WESUP_REQUIRE(h[g] == H && w[g] == W ? true : (h[g] <= H && w[g] <= W && (long)(W - 1) >= (long)(w[g] - 1)), WESUP_E_UNSUPPORTED,
                       "wesup_upsample_sum: term %d is larger than the output (only upsampling is supported)", g);
     WESUP_REQUIRE(aligned16(out) && (bias == nullptr || aligned16(bias)), WESUP_E_ALIGN, "wesup_upsample_sum: out/bias must be 16-byte aligned");
-    UpsGroups G;
-    G.n = n_terms; G.H = H; G.W = W; G.C = C;
-    for (int g = 0; g < n_terms; ++g) {
-        WESUP_REQUIRE(z[g] && aligned16(z[g]), WESUP_E_ALIGN, "wesup_upsample_sum: term %d is null or not 16-byte aligned", g);
-        WESUP_REQUIRE(h[g] > 0 && w[g] > 0 && h[g] <= H && w[g] <= W, WESUP_E_ARG, "wesup_upsample_sum: term %d has size %dx%d", g, h[g], w[g]);
-        G.src[g] = z[g]; G.h[g] = h[g]; G.w[g] = w[g];
-        G.sy[g] = bilinear_scale(h[g], H); G.sx[g] = bilinear_scale(w[g], W);
-    }
     int n_full = 0;
     for (int g = 0; g < n_terms; ++g) n_full += (h[g] == H && w[g] == W) ? 1 : 0;
     WESUP_REQUIRE(n_full <= 1 && n_terms - n_full <= UPS_LOW, WESUP_E_UNSUPPORTED,
                   "wesup_upsample_sum: at most one full-resolution and %d low-resolution terms", UPS_LOW);
-    const int seg = UPS_SEG;
+    UpsPlan G;
+    G.H = H; G.W = W; G.C = C; G.full = nullptr;
+    int n_low = 0;
+    for (int s = 0; s < UPS_LOW; ++s) { G.low[s] = nullptr; G.h[s] = 1; G.w[s] = 1; G.sy[s] = 0.f; G.sx[s] = 0.f; }
+    for (int g = 0; g < n_terms; ++g) {
+        WESUP_REQUIRE(z[g] && aligned16(z[g]), WESUP_E_ALIGN, "wesup_upsample_sum: term %d is null or not 16-byte aligned", g);
+        WESUP_REQUIRE(h[g] > 0 && w[g] > 0 && h[g] <= H && w[g] <= W, WESUP_E_ARG, "wesup_upsample_sum: term %d has size %dx%d", g, h[g], w[g]);
+        if (h[g] == H && w[g] == W) { G.full = z[g]; continue; }
+        G.low[n_low] = z[g]; G.h[n_low] = h[g]; G.w[n_low] = w[g];
+        G.sy[n_low] = bilinear_scale(h[g], H); G.sx[n_low] = bilinear_scale(w[g], W);
+        ++n_low;
+    }
     const int threads = C / V;
-    dim3 grid(cdiv(W, seg), H);
-    if (dtype == WESUP_F32)
-        upsample_sum_kernel<float><<<grid, threads, 0, stream>>>(G, bias, relu, static_cast<float *>(out));
-    else
-        upsample_sum_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>(G, bias, relu, static_cast<__nv_bfloat16 *>(out));
+    dim3 grid(cdiv(W, UPS_SEG), H);
+    if (dtype == WESUP_F32) launch_upsample_sum<float>(n_low, grid, threads, stream, G, bias, relu, out);
+    else launch_upsample_sum<__nv_bfloat16>(n_low, grid, threads, stream, G, bias, relu, out);
     WESUP_CHECK_LAUNCH("wesup_upsample_sum", 1);
     return 0;
 }
