@@ -15,6 +15,7 @@
 // segment, thread = one 16-byte channel group walking along x with the two vertically blended source columns of
 // every low-resolution term in registers (a new column is fetched only when the source index advances).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace wesup {
 
@@ -25,8 +26,8 @@ constexpr int UPS_MAX_GROUPS = 5;
 // thread (blended columns of four terms + one column of raw prefetch per term + eight pixels of the streamed term)
 // near 120, so sixteen warps stay resident per SM; with eight channels per thread only eight did and the kernel sat
 // at 0.2 of the HBM rate, stalled on its own L2 round trips.
-template <typename T> struct Raw;
-template <> struct Raw<float> {
+template <typename T, int V> struct Raw;
+template <> struct Raw<float, 4> {
     typedef uint4 type;
     static __device__ __forceinline__ uint4 zero() { return make_uint4(0u, 0u, 0u, 0u); }
     static __device__ __forceinline__ uint4 load(const float *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
@@ -43,7 +44,7 @@ template <> struct Raw<float> {
         return r;
     }
 };
-template <> struct Raw<__nv_bfloat16> {
+template <> struct Raw<__nv_bfloat16, 4> {
     typedef uint2 type;
     static __device__ __forceinline__ uint2 zero() { return make_uint2(0u, 0u); }
     static __device__ __forceinline__ uint2 load(const __nv_bfloat16 *p) { return __ldg(reinterpret_cast<const uint2 *>(p)); }
@@ -58,7 +59,20 @@ template <> struct Raw<__nv_bfloat16> {
     }
 };
 
-constexpr int UPS_V = 4;             // channels per thread
+template <> struct Raw<__nv_bfloat16, 8> {       // eight channels = one 16-byte access
+    typedef uint4 type;
+    static __device__ __forceinline__ uint4 zero() { return make_uint4(0u, 0u, 0u, 0u); }
+    static __device__ __forceinline__ uint4 load(const __nv_bfloat16 *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+    static __device__ __forceinline__ void async_copy(void *smem_dst, const __nv_bfloat16 *p) {   // 16 bytes, L2 -> shared, no L1
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(p) : "memory");
+    }
+    static __device__ __forceinline__ FVec<8> unpack(uint4 t) {
+        const float4 a = unpack_bf16x4(make_uint2(t.x, t.y)), b = unpack_bf16x4(make_uint2(t.z, t.w));
+        FVec<8> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+        return r;
+    }
+};
+
 constexpr int UPS_LOW = 4;           // low-resolution terms (plus at most one full-resolution term)
 constexpr int UPS_SEG = 64;          // output pixels per block (one row segment)
 constexpr int UPS_PX = 4;            // pixels per batch of the streamed (full-resolution) term
@@ -82,15 +96,22 @@ struct UpsPlan {                     // low-resolution terms first (slot order),
 //     pixels where nothing advances.
 // S0 accumulates one rounding per advance (<= 0.5 ulp each, ~800 along a 400-px row): ~2e-6 relative, far inside the
 // 1e-4 fp32 tolerance of the tests.
-template <typename T, int NLOW>
-__global__ void __launch_bounds__(256, 2) upsample_sum_kernel(const UpsPlan G, const float *__restrict__ bias, int relu,
-                                                              T *__restrict__ out) {
-    typedef typename Raw<T>::type raw_t;
-    constexpr int V = UPS_V;
-    constexpr int NB = sizeof(raw_t) == 16 ? 2 : 4;            // batches in flight per thread (cp.async ring in shared memory)
+// V = channels per thread: 4 (16-byte fp32 / 8-byte bf16 accesses, 256 threads) or, for bf16, 8 (16-byte accesses, 128
+// threads, more registers): everything a pixel costs a thread apart from the multiply-adds is then paid once per eight
+// channels instead of four.
+template <typename T, int V, int NLOW>
+__global__ void __launch_bounds__(1024 / V, V == 8 ? 3 : 2) upsample_sum_kernel(const UpsPlan G, const float *__restrict__ bias, int relu,
+                                                                                T *__restrict__ out) {
+    typedef Raw<T, V> RawT;
+    typedef typename RawT::type raw_t;
+    constexpr int TPB = 1024 / V;
+    constexpr int NB = sizeof(T) == 4 ? 2 : 4;                 // batches in flight per thread (cp.async ring in shared memory)
+    constexpr int PF = sizeof(T) == 4 || V == 8 ? 1 : 2;            // raw source columns requested ahead per slot (r2 ncu: half of
+                                                               // the stalls were the unpack of a column requested ONE advance
+                                                               // earlier -- under load the round trip is longer than that)
     // the streamed term never touches registers until it is used: every thread copies ITS OWN channel group of the next
     // NB batches into its own slots with cp.async (no block synchronisation: a thread only reads what it copied)
-    __shared__ raw_t s_full[NB * UPS_PX][256];
+    __shared__ raw_t s_full[NB * UPS_PX][TPB];
     __shared__ float4 s_w[UPS_SEG];            // weight of column cur+1 for the four slots
     __shared__ unsigned s_adv[UPS_SEG];        // bit s: slot s moves to its next source column AT this pixel
     __shared__ int s_first[UPS_LOW];           // source column of the segment's first pixel
@@ -119,9 +140,9 @@ __global__ void __launch_bounds__(256, 2) upsample_sum_kernel(const UpsPlan G, c
     for (int k = 0; k < V; ++k) S0.v[k] = bias != nullptr ? __ldg(bias + c + k) : 0.f;
     const T *r0[NLOW > 0 ? NLOW : 1], *r1[NLOW > 0 ? NLOW : 1];
     float wy0[NLOW > 0 ? NLOW : 1], wy1[NLOW > 0 ? NLOW : 1];
-    int nxt[NLOW > 0 ? NLOW : 1], wl[NLOW > 0 ? NLOW : 1];      // nxt: source column the raw prefetch holds (cur + 2, clamped)
+    int nxt[NLOW > 0 ? NLOW : 1], wl[NLOW > 0 ? NLOW : 1];      // nxt: last source column requested (cur + 1 + PF, clamped)
     FVec<V> R[NLOW > 0 ? NLOW : 1], D[NLOW > 0 ? NLOW : 1];      // right column (cur+1) and right - left
-    raw_t na[NLOW > 0 ? NLOW : 1], nb[NLOW > 0 ? NLOW : 1];
+    raw_t na[NLOW > 0 ? NLOW : 1][PF], nb[NLOW > 0 ? NLOW : 1][PF];
 #pragma unroll
     for (int s = 0; s < NLOW; ++s) {
         const T *src = static_cast<const T *>(G.low[s]) + c;
@@ -131,11 +152,15 @@ __global__ void __launch_bounds__(256, 2) upsample_sum_kernel(const UpsPlan G, c
         wy0[s] = ty.w0; wy1[s] = ty.w1; wl[s] = G.w[s];
         const int i0 = s_first[s];
         const int i1 = min(i0 + 1, wl[s] - 1);
-        nxt[s] = min(i0 + 2, wl[s] - 1);
-        const FVec<V> a0 = Raw<T>::unpack(Raw<T>::load(r0[s] + (long)i0 * C)), a1 = Raw<T>::unpack(Raw<T>::load(r1[s] + (long)i0 * C));
-        const FVec<V> b0 = Raw<T>::unpack(Raw<T>::load(r0[s] + (long)i1 * C)), b1 = Raw<T>::unpack(Raw<T>::load(r1[s] + (long)i1 * C));
-        na[s] = Raw<T>::load(r0[s] + (long)nxt[s] * C);
-        nb[s] = Raw<T>::load(r1[s] + (long)nxt[s] * C);
+        nxt[s] = i1;
+        const FVec<V> a0 = RawT::unpack(RawT::load(r0[s] + (long)i0 * C)), a1 = RawT::unpack(RawT::load(r1[s] + (long)i0 * C));
+        const FVec<V> b0 = RawT::unpack(RawT::load(r0[s] + (long)i1 * C)), b1 = RawT::unpack(RawT::load(r1[s] + (long)i1 * C));
+#pragma unroll
+        for (int d = 0; d < PF; ++d) {
+            nxt[s] = min(nxt[s] + 1, wl[s] - 1);
+            na[s][d] = RawT::load(r0[s] + (long)nxt[s] * C);
+            nb[s][d] = RawT::load(r1[s] + (long)nxt[s] * C);
+        }
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             const float L = fmaf(ty.w1, a1.v[k], ty.w0 * a0.v[k]);
@@ -151,7 +176,7 @@ __global__ void __launch_bounds__(256, 2) upsample_sum_kernel(const UpsPlan G, c
         if (full != nullptr) {
 #pragma unroll
             for (int j = 0; j < UPS_PX; ++j)
-                if (xs + j < x1) Raw<T>::async_copy(&s_full[(batch % NB) * UPS_PX + j][threadIdx.x], full + (long)(xs + j) * C);
+                if (xs + j < x1) RawT::async_copy(&s_full[(batch % NB) * UPS_PX + j][threadIdx.x], full + (long)(xs + j) * C);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -163,7 +188,7 @@ __global__ void __launch_bounds__(256, 2) upsample_sum_kernel(const UpsPlan G, c
         FVec<V> f[UPS_PX];
 #pragma unroll
         for (int j = 0; j < UPS_PX; ++j)                           // all-zero bits decode to 0 in both formats
-            f[j] = Raw<T>::unpack((full != nullptr && xb + j < x1) ? s_full[(batch % NB) * UPS_PX + j][threadIdx.x] : Raw<T>::zero());
+            f[j] = RawT::unpack((full != nullptr && xb + j < x1) ? s_full[(batch % NB) * UPS_PX + j][threadIdx.x] : RawT::zero());
         // refill the slots just read: the values above are in registers (unpacked), so the asynchronous writes cannot
         // overtake the reads
         issue(batch + NB);
@@ -180,10 +205,12 @@ __global__ void __launch_bounds__(256, 2) upsample_sum_kernel(const UpsPlan G, c
                     if ((adv >> s) & 1u) {
                         // an upsample advances by at most one source column per output pixel: column cur+1 becomes the
                         // left one and the prefetched raw column (in flight since the previous advance) the right one
-                        const FVec<V> p0 = Raw<T>::unpack(na[s]), p1 = Raw<T>::unpack(nb[s]);
+                        const FVec<V> p0 = RawT::unpack(na[s][0]), p1 = RawT::unpack(nb[s][0]);
+#pragma unroll
+                        for (int d = 0; d + 1 < PF; ++d) { na[s][d] = na[s][d + 1]; nb[s][d] = nb[s][d + 1]; }
                         nxt[s] = min(nxt[s] + 1, wl[s] - 1);
-                        na[s] = Raw<T>::load(r0[s] + (long)nxt[s] * C);
-                        nb[s] = Raw<T>::load(r1[s] + (long)nxt[s] * C);
+                        na[s][PF - 1] = RawT::load(r0[s] + (long)nxt[s] * C);
+                        nb[s][PF - 1] = RawT::load(r1[s] + (long)nxt[s] * C);
 #pragma unroll
                         for (int k = 0; k < V; ++k) {
                             const float rn = fmaf(wy1[s], p1.v[k], wy0[s] * p0.v[k]);
@@ -211,16 +238,16 @@ __global__ void __launch_bounds__(256, 2) upsample_sum_kernel(const UpsPlan G, c
     }
 }
 
-template <typename T>
+template <typename T, int V>
 static void launch_upsample_sum(int n_low, dim3 grid, int threads, cudaStream_t stream, const UpsPlan &G, const float *bias, int relu,
                                 void *out) {
     T *o = static_cast<T *>(out);
     switch (n_low) {
-    case 0: upsample_sum_kernel<T, 0><<<grid, threads, 0, stream>>>(G, bias, relu, o); break;
-    case 1: upsample_sum_kernel<T, 1><<<grid, threads, 0, stream>>>(G, bias, relu, o); break;
-    case 2: upsample_sum_kernel<T, 2><<<grid, threads, 0, stream>>>(G, bias, relu, o); break;
-    case 3: upsample_sum_kernel<T, 3><<<grid, threads, 0, stream>>>(G, bias, relu, o); break;
-    default: upsample_sum_kernel<T, 4><<<grid, threads, 0, stream>>>(G, bias, relu, o); break;
+    case 0: upsample_sum_kernel<T, V, 0><<<grid, threads, 0, stream>>>(G, bias, relu, o); break;
+    case 1: upsample_sum_kernel<T, V, 1><<<grid, threads, 0, stream>>>(G, bias, relu, o); break;
+    case 2: upsample_sum_kernel<T, V, 2><<<grid, threads, 0, stream>>>(G, bias, relu, o); break;
+    case 3: upsample_sum_kernel<T, V, 3><<<grid, threads, 0, stream>>>(G, bias, relu, o); break;
+    default: upsample_sum_kernel<T, V, 4><<<grid, threads, 0, stream>>>(G, bias, relu, o); break;
     }
 }
 
@@ -257,10 +284,11 @@ extern "C" int wesup_upsample_sum(const void *const *z, const int *h, const int 
         G.sy[n_low] = bilinear_scale(h[g], H); G.sx[n_low] = bilinear_scale(w[g], W);
         ++n_low;
     }
-    const int threads = C / V;
     dim3 grid(cdiv(W, UPS_SEG), H);
-    if (dtype == WESUP_F32) launch_upsample_sum<float>(n_low, grid, threads, stream, G, bias, relu, out);
-    else launch_upsample_sum<__nv_bfloat16>(n_low, grid, threads, stream, G, bias, relu, out);
+    const char *v4 = getenv("WESUP_UPS_V4");                       // cross-check / A-B of the bf16 kernels
+    if (dtype == WESUP_F32) launch_upsample_sum<float, 4>(n_low, grid, C / 4, stream, G, bias, relu, out);
+    else if (C % 8 == 0 && !(v4 && v4[0] == '1')) launch_upsample_sum<__nv_bfloat16, 8>(n_low, grid, C / 8, stream, G, bias, relu, out);
+    else launch_upsample_sum<__nv_bfloat16, 4>(n_low, grid, C / 4, stream, G, bias, relu, out);
     WESUP_CHECK_LAUNCH("wesup_upsample_sum", 1);
     return 0;
 }
