@@ -586,6 +586,21 @@ def run_train(args):
         run_step(host, i)
     ms_e2e, _ = timed(host, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    if args.trace:
+        # diagnosis only (after the timed regions): kernel timeline of two steps from the CUPTI activity records
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for i in range(2):
+                run_step(resident, i)
+            trainer.flush_metrics()
+            torch.cuda.synchronize(dev)
+        rows = sorted(((e.time_range.start, e.time_range.end - e.time_range.start, e.name[:90]) for e in prof.events()
+                       if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda r_: r_[0])
+        t0 = rows[0][0] if rows else 0
+        Path(args.trace).mkdir(parents=True, exist_ok=True)
+        with open(Path(args.trace) / f"trace_rank{rank}.tsv", "w") as fh:
+            for st_, du, nm in rows:
+                fh.write(f"{st_ - t0:.1f}\t{du:.1f}\t{nm}\n")
     value = world * ips * args.steps / (ms_total / 1e3)
     e2e_value = world * ips * args.steps / (ms_e2e / 1e3)
     peak_mem = torch.cuda.max_memory_allocated(dev) / 2**30
@@ -831,8 +846,9 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="N>1: blocking gradient all-reduce after backward instead of overlapped buckets")
     ap.add_argument("--no-dp", action="store_true", help="N>1 diagnosis: independent replicas, no gradient exchange (NOT data-parallel training)")
     ap.add_argument("--dp-at-1", action="store_true", help="N=1 diagnosis: gradients as views of the flat all-reduce buffer, no collective")
-    ap.add_argument("--bucket-mb", type=float, default=10.0, help="N>1: gradient bucket size")
+    ap.add_argument("--bucket-mb", type=float, default=40.0, help="N>1: gradient bucket size")
     ap.add_argument("--no-prefetch", action="store_true", help="preprocess inline instead of one image ahead on a side stream")
+    ap.add_argument("--trace", default=None, help="train: directory for a kernel timeline (start us, duration us, name) of two extra steps")
     ap.add_argument("--skip-cpu", action="store_true", help="omit the cpu_baseline leg (profiling runs)")
     ap.add_argument("--skip-eager", action="store_true", help="omit the gpu_eager_baseline leg")
     ap.add_argument("--skip-kernels", action="store_true", help="omit the per-kernel roofline microbench")

@@ -82,7 +82,7 @@ class BaseTrainer(ABC):
         pass
 
     # ---- data parallelism (additive) ---------------------------------------
-    def enable_data_parallel(self, process_group=None, overlap=True, bucket_mb=10.0):
+    def enable_data_parallel(self, process_group=None, overlap=True, bucket_mb=40.0):
         """Average gradients over the ranks of `process_group` every iteration: bucketed all-reduces
         started from autograd hooks while backward is still running (`overlap=False`: after backward)."""
         from ..parallel import GradientAllReduce
