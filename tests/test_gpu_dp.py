@@ -47,7 +47,7 @@ t.train_one_iteration("train", *data[0])
 got = torch.cat([p.grad.flatten() for p in t.model.parameters()])
 err = float((got - mean_g).abs().max() / (mean_g.abs().max() + 1e-30))
 ok &= err < 1e-5; notes.append(("grad_vs_mean", err))
-ok &= len(t.grad_sync.buckets) >= 4; notes.append(("buckets", len(t.grad_sync.buckets)))
+ok &= len(t.grad_sync.buckets) >= 3; notes.append(("buckets", len(t.grad_sync.buckets)))
 # (2) graph path vs eager path vs blocking path: same parameters after 7 iterations, identical on all ranks
 finals = {{}}
 for name, graph, overlap in (("graph_overlap", True, True), ("eager_overlap", False, True), ("eager_blocking", False, False)):
