@@ -92,6 +92,8 @@ def main(data_dir, model_type="wesup", checkpoint=None, output_dir=None, input_s
         output_dir = Path(checkpoint).parent.parent / "results"
         output_dir.mkdir(exist_ok=True)
     device = device or "cuda"
+    if checkpoint is not None:
+        kwargs.setdefault("pretrained", False)       # every weight comes from the checkpoint: no ImageNet download
     trainer = initialize_trainer(model_type, device=device, **kwargs)
     if checkpoint is not None:
         trainer.load_checkpoint(checkpoint)

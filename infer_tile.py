@@ -65,6 +65,8 @@ def main(data_dir, model_type="wesup", patch_size=464, checkpoint=None, output_d
     # inference never needs the (H*W,2112) tensor: superpixel means straight from the backbone levels,
     # one CUDA graph per tile shape (both can be overridden from the command line)
     kwargs = {"materialize_hypercolumn": False, "cuda_graph": True, **kwargs}
+    if checkpoint is not None:
+        kwargs.setdefault("pretrained", False)       # every weight comes from the checkpoint: no ImageNet download
     trainer = initialize_trainer(model_type, device=device, **kwargs)
     if checkpoint is not None:
         trainer.load_checkpoint(checkpoint)

@@ -240,6 +240,32 @@ def test_metrics_lag_zero_reads_in_the_same_iteration_and_nan_raises():
         lagged.flush_metrics()
 
 
+def test_nan_loss_does_not_touch_the_weights_with_lagged_metrics():
+    """metrics_lag=1 reads the loss one iteration late; the fused optimizer step is guarded on the device, so the
+    weights and the momentum of a NaN iteration stay what they were (the reference raises before backward)."""
+    trainer = initialize_trainer("wesup", device=DEV, pretrained=False)
+    trainer.optimizer, _ = trainer.get_default_optimizer()
+    b = synth.sample(96, 112, index=6, ratio=2e-3)
+    trainer.train_one_iteration("train", *b)                      # a regular step (creates the momentum buffers)
+    trainer.flush_metrics()
+    before = [p.detach().clone() for p in trainer.model.parameters()]
+    moment = [trainer.optimizer.state[p]["momentum_buffer"].clone() for p in trainer.model.parameters()]
+    real = trainer.xentropy
+    trainer.xentropy = lambda *a, **k: real(*a, **k) * float("nan")
+    trainer.train_one_iteration("train", *b)                      # NaN loss, NaN gradients: the step must be skipped
+    trainer.xentropy = real
+    with pytest.raises(ValueError, match="Loss is nan!"):
+        trainer.flush_metrics()
+    for p, q in zip(trainer.model.parameters(), before):
+        assert torch.equal(p.detach(), q)
+    for p, m in zip(trainer.model.parameters(), moment):
+        assert torch.equal(trainer.optimizer.state[p]["momentum_buffer"], m)
+    trainer.train_one_iteration("train", *b)                      # and training goes on from intact weights
+    trainer.flush_metrics()
+    assert np.isfinite(trainer.tracker.history["loss"][-1])
+    assert any(not torch.equal(p.detach(), q) for p, q in zip(trainer.model.parameters(), before))
+
+
 def test_cuda_graph_iteration_matches_the_eager_iteration():
     """cuda_graph=True: one captured graph per input shape (SLIC -> ... -> SGD step), replayed for images with
     different superpixel / labeled counts; losses, metrics and parameters follow the eager trainer's."""

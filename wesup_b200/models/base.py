@@ -127,6 +127,24 @@ class BaseTrainer(ABC):
         input_, target = self.preprocess(*data)
         self._run_iteration(phase, input_, target)
 
+    def arm_step_guard(self, loss):
+        """Device-side guard of the parameter update: with lagged metrics the host sees a NaN loss one iteration late
+        (and inside a CUDA graph the SGD step is baked in), so the fused optimizer kernel is told ON THE DEVICE to skip
+        the step when the loss -- or, with data parallelism, the averaged gradient of the last bucket, which a NaN on
+        any rank poisons -- is not finite (`found_inf`, the switch torch's GradScaler uses).  The weights and the
+        momentum stay intact and `ValueError('Loss is nan!')` still fires when the scalars reach the host.  Only the
+        fused optimizer honours it; the plain one keeps the reference's behaviour (use metrics_lag=0 there)."""
+        opt = self.optimizer
+        if opt is None or not loss.is_cuda or not opt.defaults.get("fused", False):
+            return
+        if getattr(self, "_found_inf", None) is None or self._found_inf.device != loss.device:
+            self._found_inf = torch.zeros((), dtype=torch.float32, device=loss.device)
+        opt.found_inf = self._found_inf
+        bad = ~torch.isfinite(loss.detach())
+        if self.grad_sync is not None and self.grad_sync.world_size > 1:
+            bad = bad | ~torch.isfinite(self.grad_sync.probe())
+        self._found_inf.copy_(bad.float())
+
     def _run_iteration(self, phase, input_, target):
         """Everything of `train_one_iteration` after `preprocess`."""
         if self.grad_sync is not None:
@@ -144,6 +162,7 @@ class BaseTrainer(ABC):
                     loss.backward()
                     if self.grad_sync is not None:
                         self.grad_sync.finish()          # buckets were started from the backward hooks; wait for them
+                    self.arm_step_guard(loss)
                     self.optimizer.step()
             pred, target = self.postprocess(pred, target)
             metrics.update(self.evaluate(pred, target))

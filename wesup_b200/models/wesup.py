@@ -30,7 +30,7 @@ from .base import BaseConfig, BaseTrainer
 _VGG16 = (64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M")
 
 
-def _vgg16_features(pretrained: bool) -> nn.Sequential:
+def _vgg16_features(pretrained: bool, allow_random_init: bool = False) -> nn.Sequential:
     layers, cin = [], 3
     for item in _VGG16:
         if item == "M":
@@ -40,11 +40,16 @@ def _vgg16_features(pretrained: bool) -> nn.Sequential:
             cin = item
     features = nn.Sequential(*layers)
     if pretrained:
-        try:            # ImageNet weights as in the reference; offline boxes fall back to random init
+        try:            # ImageNet weights as in the reference (models/wesup.py:198)
             from torchvision import models as tvm
             features.load_state_dict(tvm.vgg16(weights=tvm.VGG16_Weights.IMAGENET1K_V1).features.state_dict())
         except Exception as ex:  # noqa: BLE001  (URLError / OSError / missing torchvision)
-            warnings.warn(f"VGG16 ImageNet weights unavailable ({type(ex).__name__}); using random init")
+            # the reference fails here; training from scratch with the same command line gives very different
+            # results, so random init has to be asked for (pretrained=False, or allow_random_init=True)
+            if not allow_random_init:
+                raise RuntimeError(f"VGG16 ImageNet weights unavailable ({type(ex).__name__}: {ex}); pass pretrained=False "
+                                   "or allow_random_init=True to train from random initialisation") from ex
+            warnings.warn(f"VGG16 ImageNet weights unavailable ({type(ex).__name__}); using random init (allow_random_init)")
     return features
 
 
@@ -110,7 +115,8 @@ class WESUP(nn.Module):
     """Reference: models/wesup.py:182-304.
 
     Extra keyword arguments (all optional, none stored in the state_dict):
-      pretrained    load ImageNet VGG16 weights when reachable (default True)
+      pretrained    load ImageNet VGG16 weights (default True; raises when they cannot be fetched, like the reference,
+                    unless allow_random_init=True)
       hc_dtype      torch.float32 (default) or torch.bfloat16 hypercolumn storage
       hc_layout     'hwc' (default, pixel-major) or 'chw' (the reference's layout)
       fused_backward  True (default): backward of pooling + hypercolumn is one fused
@@ -138,7 +144,7 @@ class WESUP(nn.Module):
     def __init__(self, n_classes=2, D=32, **kwargs):
         super().__init__()
         self.kwargs = kwargs
-        self.backbone = _vgg16_features(kwargs.get("pretrained", True))
+        self.backbone = _vgg16_features(kwargs.get("pretrained", True), bool(kwargs.get("allow_random_init", False)))
         self.fm_channels_sum = 0
         self._side_names = []
         for layer in self.backbone:
@@ -524,6 +530,7 @@ class WESUPTrainer(BaseTrainer):
         if self.grad_sync is not None:
             self.grad_sync.finish()               # the bucketed all-reduces started by the backward hooks (captured too)
         if step:
+            self.arm_step_guard(loss)             # the update is skipped on the device when the loss is not finite
             self.optimizer.step()
         self._defer_scalars = True
         try:

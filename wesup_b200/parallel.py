@@ -202,6 +202,15 @@ class GradientAllReduce:
         self._works = []
         self._arrived = [0] * len(self.buckets)
 
+    def probe(self):
+        """0-dim tensor that is non-finite iff the reduced gradient of the head bucket is (any rank's NaN ends up in
+        every rank's average): what the trainer's device-side step guard looks at."""
+        lo, hi = self.buckets[-1]
+        _idx, flat, _views = self._small[-1]
+        if flat is not None:
+            return flat.sum()
+        return torch.stack([p.grad.sum() for p in self.params[lo:hi] if p.grad is not None]).sum()
+
     def average_gradients(self):
         """Blocking form (no overlap): one coalesced all-reduce per bucket after backward."""
         self.finish()
