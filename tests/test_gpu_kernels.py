@@ -408,6 +408,16 @@ def test_precomputed_footprint_pooling_matches_the_in_kernel_footprint_kernels(h
     finally:
         os.environ.pop("WESUP_FP_FWD")
     assert torch.isfinite(a_chunks).all() and rel_err(a_chunks, a) < tol
+    # large superpixels take several warps per (superpixel, level) list (shared-memory reduction in warp order)
+    for split in ("4", "16"):
+        os.environ["WESUP_FP_FWD_SPLIT"] = split
+        try:
+            a_split = torch.full((cap, ctot), float("nan"), device=DEV)
+            _levels_call("wesup_levels_pool_fwd_fp", ptrs, ca, ha, wa, nl, h, w, offs.data_ptr(), sp.seg_pixels.data_ptr(), cap,
+                         fp.data_ptr(), a_split.data_ptr(), st)
+        finally:
+            os.environ.pop("WESUP_FP_FWD_SPLIT")
+        assert torch.isfinite(a_split).all() and float(a_split[sp.n:].abs().max()) == 0.0 and rel_err(a_split, a) < tol
     np.testing.assert_allclose(a[:sp.n].cpu().numpy(), b.cpu().numpy(), rtol=1e-5, atol=2e-6)
     gp = torch.randn(cap, ctot, device=DEV)
     ga = [torch.full_like(s, float("nan")) for s in sides]          # every element must be overwritten

@@ -14,12 +14,13 @@ from wesup_b200.ops import SuperpixelMaps  # noqa: E402
 
 def main():
     dev = torch.device("cuda", 0)
-    H = W = bench.H
+    H = W = int(sys.argv[1]) if len(sys.argv) > 1 else bench.H
+    n_seg = int(sys.argv[2]) if len(sys.argv) > 2 else int(H * W / 200)
     lib = _lib.load()
     st = torch.cuda.current_stream().cuda_stream
     flush = bench.L2Flush(dev)
     img, _, point_mask = synth.sample(H, W, index=0)
-    labels, n = ops.slic(img.to(dev), int(H * W / 200), 40)
+    labels, n = ops.slic(img.to(dev), n_seg, 40)
     n_sp = int(n.item())
     sp = SuperpixelMaps.from_labels(labels, point_mask[0].to(dev), n_sp=n_sp)
     g = torch.Generator().manual_seed(0)
@@ -47,7 +48,7 @@ def main():
         bwd = lambda: lib.wesup_levels_pool_bwd_fp(gp.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(), ca, ha, wa,  # noqa: E731
                                                    nl, H, W, n_sp, fp.data_ptr(), gptrs, st)
         f_ms, b_ms = bench.time_kernel(fwd, 20, flush), bench.time_kernel(bwd, 20, flush)
-        print(json.dumps({"levels": name, "n": nl, "shape": list(lv[0].shape), "level_mb": round(wbytes / 1e6, 1),
+        print(json.dumps({"H": H, "n_sp": n_sp, "levels": name, "n": nl, "shape": list(lv[0].shape), "level_mb": round(wbytes / 1e6, 1),
                           "fwd_us": round(f_ms * 1e3, 1), "fwd_gbs": round(wbytes / f_ms / 1e6), "bwd_us": round(b_ms * 1e3, 1),
                           "bwd_gbs": round(wbytes / b_ms / 1e6)}))
 

@@ -9,11 +9,19 @@ import csv
 import sys
 
 
-def main(path, top=45):
+def main(path, top=45, marker=None, periods=2):
+    """`marker`: keep only the launches between the (periods+1)-th last and the last launch of the kernel whose name
+    contains it (e.g. fp_pool_fwd_cells_kernel, once per training iteration): `periods` steady-state iterations out of
+    a capture of the whole process (cuDNN autotuning, graph warm-ups and the like are cut away)."""
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
+    rows = list(csv.DictReader(lines))
+    if marker:
+        idx = [i for i, r in enumerate(rows) if marker in r["Kernel Name"]]
+        if len(idx) > periods:
+            rows = rows[idx[-periods - 1]:idx[-1]]
     tot, cnt = collections.defaultdict(float), collections.Counter()
-    for row in csv.DictReader(lines):
+    for row in rows:
         v = float(row["Metric Value"].replace(",", ""))
         unit = row["Metric Unit"]
         v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1.0)
@@ -22,7 +30,7 @@ def main(path, top=45):
         cnt[name] += 1
     total = sum(tot.values())
     ours = sum(v for k, v in tot.items() if "wesup::" in k)
-    print(f"# launch list summary: {path}\n")
+    print(f"# launch list summary: {path}" + (f" ({periods} periods of `{marker}`)" if marker else "") + "\n")
     print(f"launches: {sum(cnt.values())}; summed device time {total / 1e3:.3f} ms "
           f"(per-launch times are cold-cache and serialised under ncu: compare SHARES);")
     print(f"wesup:: kernels: {ours / 1e3:.3f} ms = {100 * ours / total:.1f} % of the captured region\n")
@@ -32,4 +40,4 @@ def main(path, top=45):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], marker=sys.argv[2] if len(sys.argv) > 2 else None, periods=int(sys.argv[3]) if len(sys.argv) > 3 else 2)

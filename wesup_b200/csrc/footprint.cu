@@ -34,7 +34,11 @@ namespace wesup {
 
 constexpr int FP_MAX_RES = 6;        // distinct non-identity resolutions (VGG16: 4)
 constexpr int FP_THREADS = 256;
-constexpr int FP_GRID_CAP = 1024;    // cells of a superpixel's low-res weight grids kept in shared memory
+constexpr int FP_GRID_CAP = 1024;    // cells of a superpixel's low-res weight grids kept in shared memory: the minimum; the
+                                     // launch sizes the (dynamic) grids from the expected superpixel extent, up to
+constexpr int FP_GRID_CAP_MAX = 16384;   // ... 192 KB.  (r2 config-3 sweep: at 2048^2 / N = 500 a superpixel's boxes hold
+                                     // ~3400 cells, nothing fitted 1024, the per-pixel fallback lists were 4x longer and
+                                     // scattered, and the forward pooling ran at 0.09 of the HBM rate)
 constexpr int FP_SLOTS = 64;         // distinct superpixels per cell footprint on the fast path
 constexpr int FP_WARPS = FP_THREADS / 32;
 
@@ -128,9 +132,10 @@ static long plan_footprint(FpPlan &P, const int *h, const int *w, int n_levels, 
 struct RInfo { int i_lo, j_lo, gw, cells, goff, lbeg, lend, base; };
 
 __global__ void __launch_bounds__(FP_THREADS) fp_build_fwd_kernel(const FpPlan P, const int32_t *__restrict__ seg_offsets,
-                                                                  const int32_t *__restrict__ seg_pixels) {
-    __shared__ unsigned grid[FP_GRID_CAP];
-    __shared__ FpEnt cellw[FP_GRID_CAP];
+                                                                  const int32_t *__restrict__ seg_pixels, int grid_cap) {
+    extern __shared__ __align__(16) unsigned char fp_dyn_smem[];
+    unsigned *grid = reinterpret_cast<unsigned *>(fp_dyn_smem);                    // grid_cap fixed-point weight sums
+    FpEnt *cellw = reinterpret_cast<FpEnt *>(fp_dyn_smem + (size_t)grid_cap * sizeof(unsigned));   // grid_cap compacted entries
     __shared__ RInfo ri[FP_MAX_RES];
     __shared__ int bbx[2];
     __shared__ int warp_cnt[FP_WARPS];
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(FP_THREADS) fp_build_fwd_kernel(const FpPlan P
                 q.j_lo = bilinear_tap(xmin, R.sx, R.w).i0;
                 const long gh = bilinear_tap(ymax, R.sy, R.h).i1 - q.i_lo + 1;
                 q.gw = bilinear_tap(xmax, R.sx, R.w).i1 - q.j_lo + 1;
-                if (off + gh * q.gw <= FP_GRID_CAP) { q.cells = (int)gh * q.gw; off += q.cells; }
+                if (off + gh * q.gw <= grid_cap) { q.cells = (int)gh * q.gw; off += q.cells; }
             }
             ri[r] = q;
         }
@@ -582,17 +587,20 @@ constexpr int FC_THREADS = 64;
 constexpr int FC_WARPS = FC_THREADS / 32;
 constexpr int FC_INFLIGHT = 8;
 
+// accumulate the 32-entry chunks first_chunk, first_chunk + chunk_stride, ... of one (superpixel, level) list; with
+// EPS > 1 entries side by side the entry groups of the warp are folded at the end (fixed order) and lanes < 32 / EPS
+// hold the sums in acc[0]
 template <int V, int EPS>
-__device__ __forceinline__ void fc_unit(const float *__restrict__ level, int Cl, const int32_t *__restrict__ px, const FpEnt *__restrict__ ent,
-                                        int ne, float inv, float *__restrict__ out, int lane) {
+__device__ __forceinline__ void fc_accumulate(const float *__restrict__ level, int Cl, const int32_t *__restrict__ px,
+                                              const FpEnt *__restrict__ ent, int ne, int lane, int first_chunk, int chunk_stride,
+                                              float4 (&acc)[V]) {
     constexpr int UF = FC_INFLIGHT / V;                     // entry slots per batch
     constexpr int LPE = 32 / EPS;                           // lanes per entry
     const int sub = lane / LPE;                             // which entry of a slot this lane reads
     const float *__restrict__ src = level + (lane - sub * LPE) * 4;
-    float4 acc[V];
 #pragma unroll
     for (int q = 0; q < V; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int e0 = 0; e0 < ne; e0 += 32) {
+    for (int e0 = 32 * first_chunk; e0 < ne; e0 += 32 * chunk_stride) {
         const int eg = e0 + lane;
         const bool valid = eg < ne;
         const int ee = valid ? eg : e0;                     // the tail repeats entry e0 with weight 0
@@ -628,6 +636,27 @@ __device__ __forceinline__ void fc_unit(const float *__restrict__ level, int Cl,
             acc[0].z += __shfl_down_sync(0xffffffffu, acc[0].z, o);
             acc[0].w += __shfl_down_sync(0xffffffffu, acc[0].w, o);
         }
+    }
+}
+
+// one (superpixel, level) unit by `split` warps (split == 1: the warp alone; else the warps of the block take the
+// list's 32-entry chunks round robin and meet in shared memory, summed in warp order => deterministic)
+template <int V, int EPS>
+__device__ __forceinline__ void fc_unit(const float *__restrict__ level, int Cl, const int32_t *__restrict__ px, const FpEnt *__restrict__ ent,
+                                        int ne, float inv, float *__restrict__ out, int lane, int wid, int split, float4 *red) {
+    constexpr int LPE = 32 / EPS;
+    float4 acc[V];
+    fc_accumulate<V, EPS>(level, Cl, px, ent, ne, lane, split > 1 ? wid : 0, split, acc);
+    if (split > 1) {
+#pragma unroll
+        for (int q = 0; q < V; ++q) red[(wid * V + q) * 32 + lane] = acc[q];
+        __syncthreads();
+        if (wid != 0) return;
+        for (int w = 1; w < split; ++w)
+#pragma unroll
+            for (int q = 0; q < V; ++q) acc[q] = acc[q] + red[(w * V + q) * 32 + lane];
+    }
+    if (EPS > 1) {
         if (lane < LPE) *reinterpret_cast<float4 *>(out + lane * 4) = inv * acc[0];
     } else {
 #pragma unroll
@@ -635,7 +664,9 @@ __device__ __forceinline__ void fc_unit(const float *__restrict__ level, int Cl,
     }
 }
 
-// levels of 32, 64, 128, 256 or 512 channels (host-checked); units are level-major, so blocks are level-homogeneous
+// levels of 32, 64, 128, 256 or 512 channels (host-checked); units are level-major, so blocks are level-homogeneous.
+// split == 1: FC_WARPS units per block, a warp each; split > 1 (large superpixels: few, long lists -- r2 config-3 sweep:
+// 7.5 ms at 2048^2 / N = 500 with one warp per unit): one unit per block of `split` warps.
 __global__ void __launch_bounds__(FC_THREADS, 12) fp_pool_fwd_cells_kernel(const Levels L, const FpPlan P, const PoolPlan F,
                                                                            const int32_t *__restrict__ seg_offsets,
                                                                            const int32_t *__restrict__ seg_pixels, int N,
@@ -663,11 +694,45 @@ __global__ void __launch_bounds__(FC_THREADS, 12) fp_pool_fwd_cells_kernel(const
     float *__restrict__ out = pooled + (long)k * L.Ctot + L.coff[l];
     const int Cl = L.C[l];
     const float *__restrict__ level = L.src[l];
-    if (Cl == 512) fc_unit<4, 1>(level, Cl, px, ent, ne, inv, out, lane);
-    else if (Cl == 256) fc_unit<2, 1>(level, Cl, px, ent, ne, inv, out, lane);
-    else if (Cl == 128) fc_unit<1, 1>(level, Cl, px, ent, ne, inv, out, lane);
-    else if (Cl == 64) fc_unit<1, 2>(level, Cl, px, ent, ne, inv, out, lane);
-    else fc_unit<1, 4>(level, Cl, px, ent, ne, inv, out, lane);
+    if (Cl == 512) fc_unit<4, 1>(level, Cl, px, ent, ne, inv, out, lane, 0, 1, nullptr);
+    else if (Cl == 256) fc_unit<2, 1>(level, Cl, px, ent, ne, inv, out, lane, 0, 1, nullptr);
+    else if (Cl == 128) fc_unit<1, 1>(level, Cl, px, ent, ne, inv, out, lane, 0, 1, nullptr);
+    else if (Cl == 64) fc_unit<1, 2>(level, Cl, px, ent, ne, inv, out, lane, 0, 1, nullptr);
+    else fc_unit<1, 4>(level, Cl, px, ent, ne, inv, out, lane, 0, 1, nullptr);
+}
+
+constexpr int FC_MAX_SPLIT = 16;
+__global__ void __launch_bounds__(32 * FC_MAX_SPLIT) fp_pool_fwd_cells_split_kernel(const Levels L, const FpPlan P, const PoolPlan F,
+                                                                                    const int32_t *__restrict__ seg_offsets,
+                                                                                    const int32_t *__restrict__ seg_pixels, int N,
+                                                                                    float *__restrict__ pooled) {
+    extern __shared__ float4 fc_red[];                      // split x V x 32 partial sums
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, split = blockDim.x >> 5;
+    const int l = (int)blockIdx.x / N;
+    const int k = (int)blockIdx.x - l * N;
+    int g = 0;
+    while (g + 1 < F.n && l >= F.g[g + 1].l0) ++g;
+    const int res = F.g[g].res;
+    const int beg = __ldg(seg_offsets + k), n_px = __ldg(seg_offsets + k + 1) - beg;
+    const int32_t *__restrict__ px = nullptr;
+    const FpEnt *__restrict__ ent = nullptr;
+    int ne = n_px;
+    if (res < 0) {
+        px = seg_pixels + beg;
+    } else {
+        const int2 span = __ldg(P.r[res].fwd_span + k);
+        ent = P.r[res].fwd_ent + span.x;
+        ne = span.y;
+    }
+    const float inv = n_px > 0 ? 1.0f / (float)n_px : 0.f;
+    float *__restrict__ out = pooled + (long)k * L.Ctot + L.coff[l];
+    const int Cl = L.C[l];
+    const float *__restrict__ level = L.src[l];
+    if (Cl == 512) fc_unit<4, 1>(level, Cl, px, ent, ne, inv, out, lane, wid, split, fc_red);
+    else if (Cl == 256) fc_unit<2, 1>(level, Cl, px, ent, ne, inv, out, lane, wid, split, fc_red);
+    else if (Cl == 128) fc_unit<1, 1>(level, Cl, px, ent, ne, inv, out, lane, wid, split, fc_red);
+    else if (Cl == 64) fc_unit<1, 2>(level, Cl, px, ent, ne, inv, out, lane, wid, split, fc_red);
+    else fc_unit<1, 4>(level, Cl, px, ent, ne, inv, out, lane, wid, split, fc_red);
 }
 
 // bwd: unit = (low-resolution cell q, group, 256-channel slice), one warp per unit, two float4 per lane;
@@ -1063,7 +1128,21 @@ extern "C" int wesup_footprint_build(const int *h, const int *w, int n_levels, i
     if (P.n == 0) return 0;                               // full-resolution levels only: nothing to precompute
     int launched = 0;
     cudaMemsetAsync(P.cursors, 0, P.cursor_bytes, stream);
-    fp_build_fwd_kernel<<<N, FP_THREADS, 0, stream>>>(P, seg_offsets, seg_pixels);
+    // shared grids: 2.5 x the cells a square superpixel of the mean area covers over all resolutions (SLIC superpixels
+    // are ragged), between FP_GRID_CAP and FP_GRID_CAP_MAX, a power of two
+    int grid_cap = FP_GRID_CAP;
+    {
+        const double side = sqrt((double)H * W / (double)N);
+        double cells = 0.0;
+        for (int r = 0; r < P.n; ++r) cells += (side * P.r[r].sy + 3.0) * (side * P.r[r].sx + 3.0);
+        while (grid_cap < FP_GRID_CAP_MAX && (double)grid_cap < 2.5 * cells) grid_cap *= 2;
+    }
+    const size_t build_smem = (size_t)grid_cap * (sizeof(unsigned) + sizeof(FpEnt));
+    if (build_smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(fp_build_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_smem);
+        WESUP_REQUIRE(e == cudaSuccess, (int)e, "wesup_footprint_build: smem attribute: %s", cudaGetErrorString(e));
+    }
+    fp_build_fwd_kernel<<<N, FP_THREADS, build_smem, stream>>>(P, seg_offsets, seg_pixels, grid_cap);
     ++launched;
     if (with_bwd) {
         int in_max = 1, blocks = 0;
@@ -1114,6 +1193,18 @@ extern "C" int wesup_levels_pool_fwd_fp(const void *const *level, const int *C, 
     bool cells = getenv("WESUP_FP_FWD") == nullptr;
     for (int l = 0; l < L.n; ++l) cells = cells && (L.C[l] == 32 || L.C[l] == 64 || L.C[l] == 128 || L.C[l] == 256 || L.C[l] == 512);
     if (cells) {
+        // warps per (superpixel, level) list: 1 while a superpixel holds < ~768 pixels (its longest list, at the
+        // full-resolution levels), else enough to keep a warp's share there, up to 16
+        int split = 1;
+        while (split < FC_MAX_SPLIT && side * side > 768.0 * split) split *= 2;
+        if (const char *e = getenv("WESUP_FP_FWD_SPLIT")) { const int v = atoi(e); if (v >= 1 && v <= FC_MAX_SPLIT) split = v; }
+        if (split > 1) {
+            const long cb = (long)L.n * N;
+            WESUP_REQUIRE(cb < (1L << 31), WESUP_E_UNSUPPORTED, "wesup_levels_pool_fwd_fp: problem too large");
+            fp_pool_fwd_cells_split_kernel<<<(int)cb, 32 * split, (size_t)split * 4 * 32 * sizeof(float4), stream>>>(L, P, F, seg_offsets, seg_pixels, N, pooled);
+            WESUP_CHECK_LAUNCH("wesup_levels_pool_fwd_fp", 1);
+            return 0;
+        }
         const long cb = (long)L.n * cdiv(N, FC_WARPS);
         WESUP_REQUIRE(cb < (1L << 31), WESUP_E_UNSUPPORTED, "wesup_levels_pool_fwd_fp: problem too large");
         fp_pool_fwd_cells_kernel<<<(int)cb, FC_THREADS, 0, stream>>>(L, P, F, seg_offsets, seg_pixels, N, pooled);

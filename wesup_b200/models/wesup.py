@@ -121,10 +121,11 @@ class WESUP(nn.Module):
       hc_layout     'hwc' (default, pixel-major) or 'chw' (the reference's layout)
       fused_backward  True (default): backward of pooling + hypercolumn is one fused
                     kernel working from the pooled gradient (hwc layout only)
-      materialize_hypercolumn  True (default): kernel (a) writes the (H*W,2112) tensor that
-                    `feature_maps` exposes, kernel (b) pools it.  False: ONE fused kernel pools
-                    straight from the side outputs (`feature_maps` stays None; needs
-                    fused_backward) -- same numbers, no 1.8 GB round trip
+      materialize_hypercolumn  False (default, the benched path): the superpixel means are pooled
+                    straight from the levels, the (H*W,2112) tensor is never written and
+                    `feature_maps` (internal to the reference's forward, models/wesup.py:246-285)
+                    stays None -- same numbers, no 1.8 GB round trip.  True: kernel (a)
+                    writes the tensor that `feature_maps` exposes, kernel (b) pools it
       pool_first    True (default; only with materialize_hypercolumn=False): the superpixel means
                     are taken from the 13 backbone conv outputs (4224 channels) and the 1x1 side
                     convolutions then run on the N pooled rows instead of on H*W pixels -- a mean
@@ -162,7 +163,7 @@ class WESUP(nn.Module):
         self.hc_dtype = kwargs.get("hc_dtype", torch.float32)
         self.hc_layout = kwargs.get("hc_layout", "hwc")
         self.fused_backward = bool(kwargs.get("fused_backward", True))
-        self.materialize_hypercolumn = bool(kwargs.get("materialize_hypercolumn", True))
+        self.materialize_hypercolumn = bool(kwargs.get("materialize_hypercolumn", False))
         self.pool_first = bool(kwargs.get("pool_first", True))
         self.use_footprints = bool(kwargs.get("footprints", True))
         self.fast_bias_grad = bool(kwargs.get("fast_bias_grad", True))
@@ -502,7 +503,9 @@ class WESUPTrainer(BaseTrainer):
     # is captured ONCE per (input shape, superpixel capacity) and replayed.  Preprocessing (H2D copy,
     # GPU SLIC, superpixel statistics) keeps running one image ahead on the side stream, which is
     # also where the host learns the image's superpixel count N without stalling.  The capacity is
-    # N rounded up to a multiple of 64: the graph's per-superpixel buffers have that many rows, the
+    # N rounded up to a multiple of max(64, 2^ceil(log2(N/32))) (64 at 464^2, 512 at CRAG size -- every capacity is a
+    # graph of its own holding a full set of activations, 30 GB at CRAG size, so images of one dataset should land
+    # on ONE capacity; r2 measured 135 GB with four): the graph's per-superpixel buffers have that many rows, the
     # rows beyond N are empty superpixels (zero features, zero labels, zero gradient), and label
     # propagation reads N and the labeled count from device memory.  Loss, metrics and updates equal
     # the eager iteration's up to fp32 summation order.  Hyper-parameters are baked into a graph;
@@ -612,6 +615,8 @@ class WESUPTrainer(BaseTrainer):
         (img, sp), (pixel_mask, _) = input_, target
         shape_key = tuple((tuple(d.shape), d.dtype) for d in data)
         q = self.GRAPH_ROW_QUANTUM
+        while q * 32 < sp.n:
+            q *= 2
         cap = -(-sp.n // q) * q
         key = (shape_key, cap)
         seen = self._graph_seen.get(shape_key, 0)
