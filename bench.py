@@ -78,7 +78,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.proc, self.gpu, self.t_begin = [], None, gpu_index, None
+
+    def mark_begin(self):
+        """The timed region starts now: only samples taken from here on count (the sampler itself is started
+        earlier -- nvidia-smi needs up to a second to deliver its first line, longer than a short timed region)."""
+        self.t_begin = time.time()
 
     def start(self):
         try:
@@ -90,14 +95,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if not any(t >= (self.t_begin or 0.0) for t, _ in self.rows):
+            time.sleep(0.25)                        # a region shorter than the sampling period: take the sample that follows it
         self.proc.terminate()
+        inside = [r for t, r in self.rows if self.t_begin is None or t >= self.t_begin]
+        if not inside and self.rows:
+            inside = [self.rows[-1][1]]             # nothing landed inside: the sample nearest to the region
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1])); mx = float(r[2])
             except (ValueError, IndexError):
@@ -576,6 +586,9 @@ def run_train(args):
         # own kernels launched in the timed region: calls through the C ABI (preprocessing) + the ones each graph replay re-issues
         return ms, lib.wesup_kernel_launches() + getattr(trainer, "replayed_launches", 0) - l0
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         run_step(resident, i)
     # cuDNN's autotuner (cudnn.benchmark) tries algorithms with multi-GB workspaces during the warm-up steps: that peak
@@ -583,9 +596,7 @@ def run_train(args):
     torch.cuda.synchronize(dev)
     peak_mem_warmup = torch.cuda.max_memory_allocated(dev) / 2**30
     torch.cuda.reset_peak_memory_stats(dev)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     ms_total, launches = timed(resident, args.steps)
     for i in range(max(1, args.warmup // 2)):
         run_step(host, i)

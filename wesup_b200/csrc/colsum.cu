@@ -37,11 +37,11 @@ __global__ void __launch_bounds__(CS_THREADS) colsum_partial_kernel(const float 
     }
 }
 
-// stage 2: block = 32 channels x 8 row lanes; lane j adds the block partials j, j + 8, ... (four independent chains in
-// flight), the eight lane sums meet in shared memory in lane order.  Fixed order => deterministic.  (r2 timeline: the
+// stage 2: block = 32 channels x 32 row lanes; lane j adds the block partials j, j + 32, ... (four independent chains in
+// flight), the 32 lane sums meet in shared memory in lane order.  Fixed order => deterministic.  (r2 timeline: the
 // first version, one thread per channel walking all ~600 partials in one dependent chain, took 12 us per call -- 13
 // calls per training iteration, three times the streaming stage it finishes.)
-constexpr int CF_LANES = 8;
+constexpr int CF_LANES = 32;
 __global__ void __launch_bounds__(32 * CF_LANES) colsum_final_kernel(const float *__restrict__ partial, int nblk, int C, float *__restrict__ out) {
     __shared__ float red[CF_LANES][32];
     const int cl = threadIdx.x & 31, j = threadIdx.x >> 5;
