@@ -591,11 +591,6 @@ def run_train(args):
         sampler.start()
     for i in range(args.warmup):
         run_step(resident, i)
-    # cuDNN's autotuner (cudnn.benchmark) tries algorithms with multi-GB workspaces during the warm-up steps: that peak
-    # is reported apart from the steady state the timed regions run in
-    torch.cuda.synchronize(dev)
-    peak_mem_warmup = torch.cuda.max_memory_allocated(dev) / 2**30
-    torch.cuda.reset_peak_memory_stats(dev)
     sampler.mark_begin()
     ms_total, launches = timed(resident, args.steps)
     for i in range(max(1, args.warmup // 2)):
@@ -619,7 +614,10 @@ def run_train(args):
                 fh.write(f"{st_ - t0:.1f}\t{du:.1f}\t{nm}\n")
     value = world * ips * args.steps / (ms_total / 1e3)
     e2e_value = world * ips * args.steps / (ms_e2e / 1e3)
+    # peak over the whole run: includes the multi-GB workspaces cuDNN's autotuner (cudnn.benchmark) tries during the
+    # warm-up steps; what the caching allocator holds when the timed regions end is reported next to it
     peak_mem = torch.cuda.max_memory_allocated(dev) / 2**30
+    reserved_end = torch.cuda.memory_reserved(dev) / 2**30
     if rank != 0:
         return end_process(world)
     del trainer, resident
@@ -683,7 +681,7 @@ def run_train(args):
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d * ips, "d2h_bytes_per_step": 4 * ips,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "gpu_eager_baseline": eager, "peak_mem_gb": peak_mem, "peak_mem_gb_warmup_incl_cudnn_autotune": peak_mem_warmup,
+            "gpu_eager_baseline": eager, "peak_mem_gb": peak_mem, "mem_reserved_gb_at_end": reserved_end,
             "kernels": kernels}
     print(json.dumps(line), flush=True)
     end_process(world)

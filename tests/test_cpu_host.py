@@ -255,3 +255,33 @@ def test_level_sizes_follow_the_backbone_arithmetic():
                 if isinstance(layer, nn.Conv2d):
                     seen.append((x.size(2), x.size(3)))
         assert model._level_sizes(h, w) == seen
+
+
+def test_gradient_bucket_plan_of_the_wesup_model():
+    """Three buckets by time of readiness: every parameter exactly once, tail of the parameter list
+    first, a small head bucket (first backbone convolutions: the last gradients of backward) of its own, and the flat
+    staging views laid out like their parameters (the fused optimizer wants matching strides)."""
+    import torch
+    from wesup_b200.models.wesup import WESUP
+    from wesup_b200.parallel import GradientAllReduce
+    model = WESUP(pretrained=False)
+    model.backbone.to(memory_format=torch.channels_last)
+    sync = GradientAllReduce(model)
+    covered = sorted(i for lo, hi in sync.buckets for i in range(lo, hi))
+    assert covered == list(range(len(sync.params)))
+    assert sync.buckets[0][1] == len(sync.params) and sync.buckets[-1][0] == 0
+    mb = [sum(p.numel() for p in sync.params[lo:hi]) * 4 / 2**20 for lo, hi in sync.buckets]
+    assert len(mb) == 3 and mb[-1] <= 8.0 and all(m <= 40.0 for m in mb) and abs(sum(mb) - 72.0) < 4.0
+    for (lo, hi), (idx, flat, views) in zip(sync.buckets, sync._small):
+        assert idx == list(range(lo, hi)) and flat.numel() == sum(sync.params[i].numel() for i in idx)
+        for i, v in zip(idx, views):
+            assert v.shape == sync.params[i].shape and v.stride() == sync.params[i].stride()
+    # the multi-tensor copy into the staging views keeps the values (channels_last weights included)
+    for p in sync.params:
+        p.grad = torch.randn_like(p)
+    before = [p.grad.clone() for p in sync.params]
+    idx, flat, views = sync._small[-1]
+    torch._foreach_copy_(views, [sync.params[i].grad for i in idx])
+    for i, v in zip(idx, views):
+        assert torch.equal(v, before[i])
+    assert torch.isfinite(sync.probe())
