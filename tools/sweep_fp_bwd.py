@@ -35,7 +35,9 @@ def main():
     gp = torch.randn(n_sp, ctot, device=dev)
     bwd = lambda: lib.wesup_levels_pool_bwd_fp(gp.data_ptr(), sp.row_labels.data_ptr(), sp.counts.data_ptr(), ca, ha, wa,  # noqa: E731
                                                13, H, W, n_sp, fp.data_ptr(), gptrs, st)
-    variants = sys.argv[1:] or ["2,3.5,0,6", "0,0,0,6", "0,99,0,6", "2,3.5,1,6", "2,3.5,2,6", "2,3.5,0,8", "0,0,0,8", "0,3.5,0,6", "0,0,1,6", "0,0,2,6"]
+    # WESUP_FP_X = "order,minb": order 0 identity blocks spread between the list blocks (default), 1 first, 2 last;
+    # minb = blocks per SM the kernel is compiled for (6: 80 registers, 8: 64 registers with spills)
+    variants = sys.argv[1:] or ["0,6", "1,6", "2,6", "0,8", "2,8"]
     for rep in range(2):
         for v in variants:
             os.environ["WESUP_FP_X"] = v
