@@ -226,6 +226,8 @@ def run_reference(args):
         return                                   # CPU arm: rank 0 alone does the work
     import torch
     from wesup_b200 import synth
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm runs on rank 0 alone and may use all host threads
+    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
     h, w = SHAPES[args.shape]
     if args.workload in ("tiles_sp", "tiles_pixel"):
         return run_reference_tiles(args)

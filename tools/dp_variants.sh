@@ -9,9 +9,8 @@ run() {
         | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value'],1), 'img/s', round(d['ms_per_step'],3), 'ms/step')"
 }
 run X=1
-run TORCH_NCCL_HIGH_PRIORITY=1
-run NCCL_MIN_NCHANNELS=32
-run TORCH_NCCL_HIGH_PRIORITY=1 NCCL_MIN_NCHANNELS=32
-EXTRA="--bucket-mb 40" run TORCH_NCCL_HIGH_PRIORITY=1
-EXTRA="--no-overlap" run NCCL_MIN_NCHANNELS=32
+run NCCL_MAX_NCHANNELS=2
+run NCCL_MAX_NCHANNELS=4
+run NCCL_MAX_NCHANNELS=8
+run NCCL_MAX_CTAS=4
 tail -3 gpurun_out/dpv/err.log
