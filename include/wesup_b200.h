@@ -209,7 +209,11 @@ int wesup_label_propagate_exact(const float *feats, int N, int D, int n_l, const
                                 void *ws, void *stream);
 /* tensor-core path (D == 32): split-TF32 tcgen05.mma cross term with TMEM
  * accumulators as a candidate filter + exact fp32 re-evaluation of the
- * survivors in the epilogue (see csrc/label_propagate_tc.cu). */
+ * survivors in the epilogue (see csrc/label_propagate_tc.cu).  Two launches:
+ * a prep kernel that splits every feature row once into the operand layout
+ * (held in `ws`: 144 bytes per 128-row-padded row + the merge buffers) and the
+ * warp-specialised pipeline (cp.async.bulk ring, four TMEM accumulators, eight
+ * epilogue warps), chained by programmatic dependent launch. */
 size_t wesup_label_propagate_tc_workspace_bytes(int N, int D, int n_l);
 int wesup_label_propagate_tc(const float *feats, int N, int D, int n_l, const float *y_l, int n_cls,
                              float thr, float *y_u, int32_t *src_idx, float *max_sim, void *ws,
@@ -234,8 +238,9 @@ int wesup_label_propagate_dev(const float *feats, int n_max, int D, const int32_
  * NULL, relu != 0 applies max(., 0).  With z[g] = cat_{levels of resolution g}(backbone level) . W'_g^T this is
  * ReLU(Linear(2112,1024)(hypercolumn)) of WESUPPixelInference.forward (models/wesup.py:392-400, :246-261) by
  * linearity of the 1x1 side convolutions, the upsampling and the Linear layer -- the GEMMs run at the levels' own
- * resolution and the (H*W, 2112) tensor is never formed.  `z`, `h`, `w` are HOST arrays.  C % 4 == 0 (fp32) or
- * C % 8 == 0 (bf16), C <= 1024 / 2048. */
+ * resolution and the (H*W, 2112) tensor is never formed.  `z`, `h`, `w` are HOST arrays.  C % 4 == 0, C <= 1024
+ * (bf16 with C % 8 == 0 takes the 8-channels-per-thread kernel).  At most one full-resolution and four
+ * low-resolution terms. */
 int wesup_upsample_sum(const void *const *z, const int *h, const int *w, int n_terms, int H, int W, int C,
                        int dtype, const float *bias, int relu, void *out, void *stream);
 
