@@ -211,7 +211,7 @@ int wesup_label_propagate_exact(const float *feats, int N, int D, int n_l, const
  * accumulators as a candidate filter + exact fp32 re-evaluation of the
  * survivors in the epilogue (see csrc/label_propagate_tc.cu).  Two launches:
  * a prep kernel that splits every feature row once into the operand layout
- * (held in `ws`: 144 bytes per 128-row-padded row + the merge buffers) and the
+ * (held in `ws`: 288 bytes per 128-row-padded row + the merge buffers) and the
  * warp-specialised pipeline (cp.async.bulk ring, four TMEM accumulators, eight
  * epilogue warps), chained by programmatic dependent launch. */
 size_t wesup_label_propagate_tc_workspace_bytes(int N, int D, int n_l);
