@@ -542,11 +542,9 @@ extern "C" int wesup_label_propagate_tc(const float *feats, int N, int D, int n_
     float *tile_nbmax = reinterpret_cast<float *>(base + Y.off_nbmax);
     uint32_t *a_tiles = reinterpret_cast<uint32_t *>(base + Y.off_a);
     uint32_t *b_tiles = reinterpret_cast<uint32_t *>(base + Y.off_b);
-    static bool configured = false;
-    if (!configured) {
+    {   // per call, like the other kernels: the attribute belongs to the current device, a process may drive several
         cudaError_t e = cudaFuncSetAttribute(label_propagate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcShared));
         WESUP_REQUIRE(e == cudaSuccess, (int)e, "wesup_label_propagate_tc: smem attribute: %s", cudaGetErrorString(e));
-        configured = true;
     }
     label_propagate_tc_prep_kernel<<<Y.tiles_l + Y.row_blocks, TC_M, 0, stream>>>(feats, n_l, Y.n_u, Y.tiles_l, a_tiles, b_tiles, tile_nbmax,
                                                                                    reinterpret_cast<uint32_t *>(base), (int)(Y.head_bytes / 4));
