@@ -285,3 +285,35 @@ def test_gradient_bucket_plan_of_the_wesup_model():
     for i, v in zip(idx, views):
         assert torch.equal(v, before[i])
     assert torch.isfinite(sync.probe())
+
+
+def test_folded_first_layer_equals_the_reference_order_of_operations():
+    """Host logic of pixel-wise inference without the hypercolumn (models/wesup.py:246-261, :392-400): side conv ->
+    bilinear upsample (align_corners) -> concat -> Linear(2112, 1024) equals, by linearity, the sum over level
+    resolutions of the upsampled products with the folded weights plus the folded bias.  Checked on the CPU in fp64
+    with F.interpolate standing in for the CUDA kernel `wesup_upsample_sum`."""
+    import torch
+    import torch.nn.functional as F
+    from wesup_b200.models.wesup import WESUPPixelInference
+    torch.manual_seed(3)
+    model = WESUPPixelInference(pretrained=False).double().eval()
+    x = torch.rand(1, 3, 40, 56, dtype=torch.float64)
+    with torch.no_grad():
+        outs = model._backbone_levels(x)
+        size = (x.size(2), x.size(3))
+        # the reference's order: 13 side convolutions, upsample each, concatenate, first Linear
+        sides = [getattr(model, n)(o) for n, o in zip(model._side_names, outs)]
+        hyper = torch.cat([F.interpolate(s, size, mode="bilinear", align_corners=True) for s in sides], dim=1)
+        ref = model.fc_layers[0](hyper[0].permute(1, 2, 0).reshape(-1, hyper.size(1)))
+        # the folded order: one product per resolution at the level's own size, upsample, sum, folded bias
+        groups, bias = model._folded_first_layer(outs, torch.float64)
+        assert len(groups) == 5 and [w.size(1) for _, w, _ in groups] == [128, 256, 768, 1536, 1536]
+        total = bias.view(1, -1, 1, 1).double()
+        for (gh, gw), w_g, levels in groups:
+            rows = torch.cat([o.permute(0, 2, 3, 1).reshape(-1, o.size(1)) for o in levels], dim=1)
+            z = F.linear(rows, w_g.double()).view(1, gh, gw, -1).permute(0, 3, 1, 2)
+            total = total + (z if (gh, gw) == size else F.interpolate(z, size, mode="bilinear", align_corners=True))
+        got = total[0].permute(1, 2, 0).reshape(-1, total.size(1))
+    assert got.shape == ref.shape == (40 * 56, 1024)
+    # the folding itself runs in fp32 (the weights' dtype): agreement to fp32 rounding of the folded weights
+    assert float((got - ref).abs().max()) < 1e-6 * max(1.0, float(ref.abs().max()))
